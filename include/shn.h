@@ -1,0 +1,134 @@
+/* include/shn.h — C ABI of libshn_b200.so: the B200-native HNSW search / construction engine that replaces
+ * the compute-node hot path of SHINE (TianqiLiu-777/DM-HNSW-reference).
+ *
+ * The reference has no FFI; its hot path is reached through C++ templates inside the `shine` binary.  Each
+ * entry point below names the reference interface it stands in for (paths relative to the reference tree).
+ * A host program keeps the reference's process contract (CLI, dataset directory, index dumps, JSON on
+ * stdout — see dm-hnsw-reference_b200/host/ and INTEGRATION.md) and calls this ABI at the two places where
+ * the reference calls run_inserts (src/compute_node.cc:80) and run_queries (src/compute_node.cc:238).
+ *
+ * Conventions: plain pointers and sizes only; every int return is 0 on success, <0 on error, with a
+ * thread-local message available from shn_last_error().  The caller owns every buffer it passes; the handle
+ * owns all device memory and streams.  One handle may be used by one host thread at a time.  There is no CPU
+ * fallback: every call fails with SHN_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef SHN_H
+#define SHN_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct shn_index shn_index; /* opaque */
+
+typedef enum { SHN_L2 = 0, SHN_IP = 1 } shn_metric; /* src/hnsw/distance.hh:153 L2Distance, :157 IPDistance */
+
+enum {
+  SHN_OK = 0,
+  SHN_ERR_ARG = -1,      /* invalid argument (e.g. ef < k: src/hnsw/hnsw.hh:36) */
+  SHN_ERR_IO = -2,       /* file missing / unreadable / not a dump for this dim and m */
+  SHN_ERR_CUDA = -3,     /* CUDA error or no usable device */
+  SHN_ERR_CAPACITY = -4, /* a per-query structure overflowed (visited set); results of that call are invalid */
+  SHN_ERR_STATE = -5     /* operation not valid for this handle */
+};
+
+/* Counters with the meaning of statistics::ThreadStatistics (src/common/statistics.hh:148-176), summed over
+ * the queries (or inserts) of one call, plus device timing. */
+typedef struct {
+  uint64_t distcomps;             /* hnsw.hh:272,286,376,459 */
+  uint64_t visited_nodes;         /* levels > 0  (hnsw.hh:270,365) */
+  uint64_t visited_nodes_l0;      /* level 0     (hnsw.hh:270,442) */
+  uint64_t visited_neighborlists; /* hnsw.hh:359,438 */
+  uint64_t lists_l0;              /* the level-0 share of visited_neighborlists */
+  uint64_t lists_upper;           /* the upper-level share */
+  uint64_t algorithmic_bytes;     /* 4*dim*distcomps + 4*(2m)*lists_l0 + 4*m*lists_upper   */
+  uint64_t reference_layout_bytes;/* what the reference counts in rdma_reads_in_bytes for the same work (rdma_reads.hh:12,46) */
+  uint64_t overflow_queries;      /* queries whose visited set spilled to the HBM table (still exact) */
+  uint64_t processed;             /* statistics.hh processed */
+  double kernel_ms;               /* CUDA-event time of the device work of this call */
+  double h2d_ms, d2h_ms;          /* host<->device copies of this call (0 for the *_device entry points) */
+} shn_stats;
+
+/* ---- index lifetime -------------------------------------------------------------------------------------- */
+
+/* Load an index from reference-format dumps dump/index_m<M>_efc<efC>_node<i>_of<n>.dat, one per memory node
+ * (written by src/memory_node.hh:187-195, path built in src/compute_node.cc:428-430; format: SURVEY App. B).
+ * Replaces MemoryNode::store_or_load_index load branch (memory_node.hh:182) + the RDMA READ path: nodes of
+ * memory node i become rows in HBM.  dim and m are not stored in the file (io/read_data.hh:35-40). */
+int shn_index_load(shn_index** out, const char* const* dump_paths, int n_parts, uint32_t dim, uint32_t m,
+                   shn_metric metric, int gpu_id);
+/* Same, from dumps already in host memory. */
+int shn_index_load_mem(shn_index** out, const void* const* dumps, const uint64_t* sizes, int n_parts, uint32_t dim,
+                       uint32_t m, shn_metric metric, int gpu_id);
+
+/* Build an index over base[n][dim] (host, row-major fp32; ids[i] = external id of row i, NULL = i) on the GPU.
+ * Replaces ComputeNode::run_inserts -> hnsw::schedule<D,true> -> HNSW::insert (compute_node.cc:322,
+ * hnsw/scheduler.hh:20, hnsw/hnsw.hh:40-251).  Levels are drawn with the reference's recipe
+ * floor(-ln(U)/ln(m)) from mt19937(seed) (hnsw.hh:48,563).  The graph is not the reference's graph (insertion
+ * is batched); it meets the same recall at equal m / ef_construction / ef. */
+int shn_index_build(shn_index** out, const float* base, const uint32_t* ids, uint64_t n, uint32_t dim, uint32_t m,
+                    uint32_t ef_construction, shn_metric metric, uint32_t seed, int gpu_id);
+/* Same with base already in device memory on gpu_id (row stride = dim floats). */
+int shn_index_build_device(shn_index** out, const float* d_base, const uint32_t* d_ids, uint64_t n, uint32_t dim,
+                           uint32_t m, uint32_t ef_construction, shn_metric metric, uint32_t seed, int gpu_id);
+
+/* Write the index as n_parts reference-format dumps (nodes dealt round-robin to parts when n_parts > 1).
+ * Replaces MemoryNode::store_or_load_index store branch (memory_node.hh:187-195). */
+int shn_index_store(const shn_index*, const char* const* dump_paths, int n_parts);
+/* Size query + in-memory variant: sizes[i] receives the byte size of part i; if dumps != NULL, dumps[i] must
+ * point to sizes[i] writable bytes. */
+int shn_index_store_mem(const shn_index*, void* const* dumps, uint64_t* sizes, int n_parts);
+
+void shn_index_free(shn_index*);
+
+/* ---- introspection ----------------------------------------------------------------------------------------- */
+uint64_t shn_index_size(const shn_index*);       /* number of nodes */
+uint32_t shn_index_dim(const shn_index*);
+uint32_t shn_index_m(const shn_index*);
+uint32_t shn_index_max_level(const shn_index*);  /* build.max_level in the reference's JSON */
+uint64_t shn_index_hbm_bytes(const shn_index*);  /* device memory held by the handle */
+uint64_t shn_index_dump_bytes(const shn_index*); /* "index_size": bytes the reference would have allocated (rdma_atomics.hh:98) */
+/* Build-time counters of a handle created by shn_index_build (zero for loaded handles). */
+int shn_index_build_stats(const shn_index*, shn_stats* out);
+
+/* Options: "exact_arith" (0/1, default 0): compute distances in the reference's summation order
+ * (src/hnsw/distance.hh as compiled, see oracle/hnsw_oracle.c) so that results are bit-identical to the
+ * reference's; 0 = warp-parallel summation (ULP-level differences).  "warps_per_sm" (0 = auto). */
+int shn_set_option(shn_index*, const char* key, int64_t value);
+
+/* ---- search ------------------------------------------------------------------------------------------------ */
+
+/* k-NN for nq queries: HNSW::knn (hnsw/hnsw.hh:253-307) for every slot that hnsw::schedule<D,false>
+ * (hnsw/scheduler.hh:66-75) would dequeue.  queries/out_* are HOST buffers; the call returns when the results
+ * are in host memory.  out_ids[q*k + i] = external id (node uid, node/node.hh:81) of the i-th nearest result,
+ * ascending by distance (the reference returns the same set in heap-array order without distances,
+ * hnsw.hh:300-303), padded with 0xFFFFFFFF / +inf when fewer than k nodes are reachable.
+ * out_dists may be NULL.  stats may be NULL. */
+int shn_search(shn_index*, const float* queries, uint64_t nq, uint32_t k, uint32_t ef, uint32_t* out_ids,
+               float* out_dists, shn_stats* stats);
+
+/* Same with every buffer resident in the HBM of the index's GPU; `stream` is a cudaStream_t (NULL = the
+ * handle's own stream).  Asynchronous unless stats != NULL.  per_query_counters (device, may be NULL) receives 6
+ * u32 per query: distcomps, visited_nodes, visited_nodes_l0, lists_l0, lists_upper, overflow flag. */
+int shn_search_device(shn_index*, const float* d_queries, uint64_t nq, uint32_t k, uint32_t ef, uint32_t* d_out_ids,
+                      float* d_out_dists, uint32_t* d_per_query_counters, void* stream, shn_stats* stats);
+
+/* ---- ground truth ------------------------------------------------------------------------------------------ */
+
+/* Exact top-k by brute force (the reference only reads ground truth produced offline, compute_node.cc:317,588).
+ * Host buffers; distances are fp32 squared L2 or 1 - dot, ties broken by lower id. */
+int shn_bruteforce_topk(const float* base, uint64_t n, const float* queries, uint64_t nq, uint32_t dim,
+                        shn_metric metric, uint32_t k, uint32_t* out_ids, float* out_dists, int gpu_id);
+int shn_bruteforce_topk_device(const float* d_base, uint64_t n, const float* d_queries, uint64_t nq, uint32_t dim,
+                               shn_metric metric, uint32_t k, uint32_t* d_out_ids, float* d_out_dists, int gpu_id,
+                               void* stream);
+
+const char* shn_last_error(void);
+const char* shn_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SHN_H */
