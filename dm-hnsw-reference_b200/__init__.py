@@ -1,0 +1,9 @@
+"""dm-hnsw-reference_b200 — B200-native HNSW search engine behind the SHINE compute-node contract.
+
+The product is libshn_b200.so (hand-written sm_100a CUDA + a C ABI, include/shn.h) and the host binary
+host/shine_b200; this Python package is only the ctypes binding the tests and bench.py drive it through.
+The directory name is not an importable identifier: load it with `load_package()` from __graft_entry__.py or
+put this directory on sys.path and `import shn`.
+"""
+from . import shn  # noqa: F401
+from .shn import Index, ShnError, build_library, library_path, repartition_dumps  # noqa: F401

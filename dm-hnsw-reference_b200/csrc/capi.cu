@@ -1,0 +1,416 @@
+// capi.cu — the C ABI of libshn_b200.so (include/shn.h).  Owns the index handle: device arrays, stream, scratch.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/shn.h"
+#include "engine.h"
+
+using namespace shn;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CU(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e__ = (call);                                                                      \
+    if (e__ != cudaSuccess) return fail(SHN_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e__));  \
+  } while (0)
+
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  cudaError_t ensure(size_t want) {
+    if (want <= n) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; n = 0;
+    cudaError_t e = cudaMalloc(&p, want * sizeof(T));
+    if (e == cudaSuccess) n = want;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+
+}  // namespace
+
+struct shn_index {
+  int gpu = 0;
+  int num_sms = 0;
+  shn_metric metric = SHN_L2;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+
+  // graph in HBM (graph.h)
+  uint32_t n = 0, dim = 0, m = 0, row_f4 = 0, ep_row = kInvalid, max_level = 0;
+  uint64_t n_up = 0;
+  float4* d_vec = nullptr;
+  uint32_t* d_l0 = nullptr;
+  uint32_t* d_up_base = nullptr;
+  uint32_t* d_up = nullptr;
+  uint32_t* d_ext_id = nullptr;
+  uint32_t* d_level = nullptr;
+  uint64_t hbm_bytes = 0, dump_bytes = 0;
+
+  // scratch
+  SearchWorkspace ws;
+  DevBuf<uint32_t> ovf;
+  DevBuf<float> q_stage, dist_stage;
+  DevBuf<uint32_t> id_stage;
+  int warps_per_sm = 0;
+
+  DeviceGraph view() const {
+    DeviceGraph g;
+    g.vec = d_vec; g.l0 = d_l0; g.up_base = d_up_base; g.up = d_up; g.ext_id = d_ext_id;
+    g.n = n; g.dim = dim; g.m = m; g.m0 = 2 * m; g.row_f4 = row_f4; g.ep_row = ep_row; g.ep_level = max_level_of_ep;
+    return g;
+  }
+  uint32_t max_level_of_ep = 0;
+};
+
+namespace {
+
+int select_device(int gpu_id, int* num_sms) {
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return fail(SHN_ERR_CUDA, "no CUDA device is usable (%s); libshn_b200 has no CPU path", cudaGetErrorString(e));
+  if (gpu_id < 0 || gpu_id >= count) return fail(SHN_ERR_ARG, "gpu_id %d out of range (%d devices)", gpu_id, count);
+  CU(cudaSetDevice(gpu_id));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, gpu_id));
+  if (prop.major != 10)
+    return fail(SHN_ERR_CUDA, "device %d is sm_%d%d; libshn_b200 is built for sm_100a only", gpu_id, prop.major, prop.minor);
+  *num_sms = prop.multiProcessorCount;
+  return SHN_OK;
+}
+
+// Move a parsed graph into HBM in the layout of graph.h.
+int upload(shn_index* ix, const HostGraph& g) {
+  ix->n = g.n; ix->dim = g.dim; ix->m = g.m; ix->ep_row = g.ep_row; ix->max_level = g.max_level; ix->n_up = g.n_up;
+  ix->max_level_of_ep = g.level[g.ep_row];
+  ix->row_f4 = ((g.dim + 3) / 4 + 1) & ~1u;  // whole 32-byte sectors per row
+  const size_t row_floats = static_cast<size_t>(ix->row_f4) * 4;
+  const size_t m0 = 2ull * g.m;
+  CU(cudaMalloc(&ix->d_vec, g.n * row_floats * sizeof(float)));
+  CU(cudaMalloc(&ix->d_l0, g.n * m0 * sizeof(uint32_t)));
+  CU(cudaMalloc(&ix->d_up_base, g.n * sizeof(uint32_t)));
+  CU(cudaMalloc(&ix->d_up, std::max<size_t>(g.n_up, 1) * g.m * sizeof(uint32_t)));
+  CU(cudaMalloc(&ix->d_ext_id, g.n * sizeof(uint32_t)));
+  CU(cudaMalloc(&ix->d_level, g.n * sizeof(uint32_t)));
+  ix->hbm_bytes = g.n * (row_floats * 4 + m0 * 4 + 12) + std::max<size_t>(g.n_up, 1) * g.m * 4;
+  if (row_floats == g.dim) {
+    CU(cudaMemcpyAsync(ix->d_vec, g.vec.data(), g.n * row_floats * sizeof(float), cudaMemcpyHostToDevice, ix->stream));
+  } else {
+    CU(cudaMemsetAsync(ix->d_vec, 0, g.n * row_floats * sizeof(float), ix->stream));
+    CU(cudaMemcpy2DAsync(ix->d_vec, row_floats * sizeof(float), g.vec.data(), g.dim * sizeof(float), g.dim * sizeof(float),
+                         g.n, cudaMemcpyHostToDevice, ix->stream));
+  }
+  CU(cudaMemcpyAsync(ix->d_l0, g.l0.data(), g.n * m0 * sizeof(uint32_t), cudaMemcpyHostToDevice, ix->stream));
+  CU(cudaMemcpyAsync(ix->d_up_base, g.up_base.data(), g.n * sizeof(uint32_t), cudaMemcpyHostToDevice, ix->stream));
+  if (g.n_up) CU(cudaMemcpyAsync(ix->d_up, g.up.data(), g.n_up * g.m * sizeof(uint32_t), cudaMemcpyHostToDevice, ix->stream));
+  CU(cudaMemcpyAsync(ix->d_ext_id, g.uid.data(), g.n * sizeof(uint32_t), cudaMemcpyHostToDevice, ix->stream));
+  CU(cudaMemcpyAsync(ix->d_level, g.level.data(), g.n * sizeof(uint32_t), cudaMemcpyHostToDevice, ix->stream));
+  CU(cudaStreamSynchronize(ix->stream));
+  uint64_t db = 0;
+  for (uint32_t r = 0; r < g.n; ++r) db += ref_alloc_bytes(g.dim, g.m, g.level[r]);
+  ix->dump_bytes = db;
+  return SHN_OK;
+}
+
+int download(const shn_index* ix, HostGraph& g) {
+  g = HostGraph{};
+  g.n = ix->n; g.dim = ix->dim; g.m = ix->m; g.ep_row = ix->ep_row; g.max_level = ix->max_level; g.n_up = ix->n_up;
+  const size_t row_floats = static_cast<size_t>(ix->row_f4) * 4, m0 = 2ull * ix->m;
+  g.vec.resize(static_cast<size_t>(g.n) * g.dim);
+  g.uid.resize(g.n); g.level.resize(g.n); g.up_base.resize(g.n);
+  g.l0.resize(g.n * m0);
+  g.up.resize(g.n_up * g.m);
+  CU(cudaSetDevice(ix->gpu));
+  CU(cudaStreamSynchronize(ix->stream));
+  CU(cudaMemcpy2D(g.vec.data(), g.dim * sizeof(float), ix->d_vec, row_floats * sizeof(float), g.dim * sizeof(float), g.n,
+                  cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(g.l0.data(), ix->d_l0, g.n * m0 * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(g.up_base.data(), ix->d_up_base, g.n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  if (g.n_up) CU(cudaMemcpy(g.up.data(), ix->d_up, g.n_up * g.m * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(g.uid.data(), ix->d_ext_id, g.n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(g.level.data(), ix->d_level, g.n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  return SHN_OK;
+}
+
+int new_handle(shn_index** out, int gpu_id, shn_metric metric) {
+  int sms = 0;
+  int rc = select_device(gpu_id, &sms);
+  if (rc != SHN_OK) return rc;
+  shn_index* ix = new shn_index();
+  ix->gpu = gpu_id; ix->num_sms = sms; ix->metric = metric;
+  cudaError_t e = cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking);
+  for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreate(&ix->ev[i]);
+  if (e == cudaSuccess) e = cudaMalloc(&ix->ws.counter, sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaMalloc(&ix->ws.totals, kNumTotals * sizeof(unsigned long long));
+  if (e != cudaSuccess) {
+    shn_index_free(ix);
+    return fail(SHN_ERR_CUDA, "handle setup: %s", cudaGetErrorString(e));
+  }
+  *out = ix;
+  return SHN_OK;
+}
+
+bool read_file(const char* path, std::vector<uint8_t>& out, std::string& err) {
+  FILE* f = std::fopen(path, "rb");
+  if (!f) { err = std::string("cannot open ") + path; return false; }
+  std::fseek(f, 0, SEEK_END);
+  const long sz = std::ftell(f);
+  std::fseek(f, 0, SEEK_SET);
+  if (sz < 0) { std::fclose(f); err = std::string("cannot size ") + path; return false; }
+  out.resize(static_cast<size_t>(sz));
+  const size_t got = sz ? std::fread(out.data(), 1, out.size(), f) : 0;
+  std::fclose(f);
+  if (got != out.size()) { err = std::string("short read on ") + path; return false; }
+  return true;
+}
+
+// Overflow tables: one per warp slot of the launch, sized from ef.
+int prepare_workspace(shn_index* ix, const SearchConfig& cfg, uint32_t nq) {
+  int grid, block;
+  size_t smem;
+  uint32_t vis_cap;
+  const DeviceGraph g = ix->view();
+  cudaError_t e = search_plan(g, cfg, nq, &grid, &block, &smem, &vis_cap);
+  if (e == cudaErrorInvalidValue) return fail(SHN_ERR_ARG, "ef=%u / dim=%u do not fit the per-warp shared-memory budget", cfg.ef, g.dim);
+  if (e != cudaSuccess) return fail(SHN_ERR_CUDA, "search_plan: %s", cudaGetErrorString(e));
+  uint32_t ovf_cap = 1024;
+  while (ovf_cap < 64u * cfg.ef) ovf_cap <<= 1;
+  if (ovf_cap > (1u << 17)) ovf_cap = 1u << 17;
+  if (ovf_cap > 4 * ix->n) { ovf_cap = 1024; while (ovf_cap < 4 * ix->n) ovf_cap <<= 1; }
+  const uint32_t slots = static_cast<uint32_t>(grid) * (block / 32);
+  if (ix->ws.ovf_cap != ovf_cap || ix->ws.ovf_slots < slots) {
+    const size_t words = static_cast<size_t>(slots) * ovf_cap;
+    if (ix->ovf.ensure(words) != cudaSuccess) return fail(SHN_ERR_CUDA, "cannot allocate %zu bytes of visited-set overflow", words * 4);
+    CU(cudaMemsetAsync(ix->ovf.p, 0xFF, ix->ovf.n * sizeof(uint32_t), ix->stream));
+    CU(cudaStreamSynchronize(ix->stream));
+    ix->ws.ovf = ix->ovf.p; ix->ws.ovf_cap = ovf_cap; ix->ws.ovf_slots = static_cast<uint32_t>(ix->ovf.n / ovf_cap);
+  }
+  return SHN_OK;
+}
+
+void fill_stats(const shn_index* ix, const unsigned long long* t, uint64_t nq, shn_stats* s) {
+  s->distcomps = t[kDistcomps];
+  s->visited_nodes = t[kVisitedUpper];
+  s->visited_nodes_l0 = t[kVisitedL0];
+  s->lists_l0 = t[kListsL0];
+  s->lists_upper = t[kListsUpper];
+  s->visited_neighborlists = t[kListsL0] + t[kListsUpper];
+  s->algorithmic_bytes = 4ull * ix->dim * t[kDistcomps] + 4ull * (2 * ix->m) * t[kListsL0] + 4ull * ix->m * t[kListsUpper];
+  // node READs = distcomps - 1 per query (hnsw.hh:271,285 share one READ); lists at their fixed slot sizes
+  s->reference_layout_bytes = ref_node_bytes(ix->dim) * (t[kDistcomps] - nq) + ref_list0_bytes(ix->m) * t[kListsL0] +
+                              ref_listu_bytes(ix->m) * t[kListsUpper];
+  s->overflow_queries = t[kOverflowQueries];
+  s->processed = nq;
+}
+
+int run_search(shn_index* ix, const float* d_queries, uint64_t nq, uint32_t k, uint32_t ef, uint32_t* d_ids, float* d_dists,
+               uint32_t* d_per_query, cudaStream_t stream, bool timed) {
+  SearchConfig cfg;
+  cfg.k = k; cfg.ef = ef; cfg.ip = ix->metric == SHN_IP; cfg.warps_per_sm = ix->warps_per_sm; cfg.num_sms = ix->num_sms;
+  int rc = prepare_workspace(ix, cfg, static_cast<uint32_t>(nq));
+  if (rc != SHN_OK) return rc;
+  if (timed) CU(cudaEventRecord(ix->ev[1], stream));
+  cudaError_t e = search_launch(ix->view(), cfg, d_queries, static_cast<uint32_t>(nq), d_ids, d_dists, d_per_query, ix->ws, stream);
+  if (e != cudaSuccess) return fail(SHN_ERR_CUDA, "search_launch: %s", cudaGetErrorString(e));
+  if (timed) CU(cudaEventRecord(ix->ev[2], stream));
+  return SHN_OK;
+}
+
+int check_search_args(const shn_index* ix, uint64_t nq, uint32_t k, uint32_t ef) {
+  if (!ix) return fail(SHN_ERR_ARG, "null index handle");
+  if (k == 0) return fail(SHN_ERR_ARG, "k must be positive");
+  if (ef < k) return fail(SHN_ERR_ARG, "ef_search must be >= k (hnsw.hh:36): ef=%u k=%u", ef, k);
+  if (ef > 4096) return fail(SHN_ERR_ARG, "ef_search %u exceeds the supported maximum 4096", ef);
+  if (nq >= kInvalid) return fail(SHN_ERR_ARG, "too many queries in one call");
+  return SHN_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int shn_index_load_mem(shn_index** out, const void* const* dumps, const uint64_t* sizes, int n_parts, uint32_t dim,
+                       uint32_t m, shn_metric metric, int gpu_id) {
+  if (!out || !dumps || !sizes) return fail(SHN_ERR_ARG, "null argument");
+  if (n_parts < 1 || dim == 0 || m == 0 || m > 32) return fail(SHN_ERR_ARG, "need n_parts >= 1, dim >= 1, 1 <= m <= 32");
+  HostGraph g;
+  std::string err;
+  if (!parse_dumps(dumps, sizes, n_parts, dim, m, g, err)) return fail(SHN_ERR_IO, "%s", err.c_str());
+  shn_index* ix = nullptr;
+  int rc = new_handle(&ix, gpu_id, metric);
+  if (rc != SHN_OK) return rc;
+  rc = upload(ix, g);
+  if (rc != SHN_OK) { shn_index_free(ix); return rc; }
+  *out = ix;
+  return SHN_OK;
+}
+
+int shn_index_load(shn_index** out, const char* const* dump_paths, int n_parts, uint32_t dim, uint32_t m,
+                   shn_metric metric, int gpu_id) {
+  if (!out || !dump_paths || n_parts < 1) return fail(SHN_ERR_ARG, "null argument");
+  std::vector<std::vector<uint8_t>> bufs(n_parts);
+  std::vector<const void*> ptrs(n_parts);
+  std::vector<uint64_t> sizes(n_parts);
+  for (int i = 0; i < n_parts; ++i) {
+    std::string err;
+    if (!read_file(dump_paths[i], bufs[i], err)) return fail(SHN_ERR_IO, "%s", err.c_str());
+    ptrs[i] = bufs[i].data();
+    sizes[i] = bufs[i].size();
+  }
+  return shn_index_load_mem(out, ptrs.data(), sizes.data(), n_parts, dim, m, metric, gpu_id);
+}
+
+int shn_index_store_mem(const shn_index* ix, void* const* dumps, uint64_t* sizes, int n_parts) {
+  if (!ix || !sizes || n_parts < 1 || n_parts > 65535) return fail(SHN_ERR_ARG, "bad arguments");
+  HostGraph g;
+  int rc = download(ix, g);
+  if (rc != SHN_OK) return rc;
+  dump_sizes(g, n_parts, sizes);
+  if (dumps) emit_dumps(g, n_parts, dumps);
+  return SHN_OK;
+}
+
+int shn_index_store(const shn_index* ix, const char* const* dump_paths, int n_parts) {
+  if (!ix || !dump_paths || n_parts < 1 || n_parts > 65535) return fail(SHN_ERR_ARG, "bad arguments");
+  HostGraph g;
+  int rc = download(ix, g);
+  if (rc != SHN_OK) return rc;
+  std::vector<uint64_t> sizes(n_parts);
+  dump_sizes(g, n_parts, sizes.data());
+  std::vector<std::vector<uint8_t>> bufs(n_parts);
+  std::vector<void*> ptrs(n_parts);
+  for (int i = 0; i < n_parts; ++i) { bufs[i].resize(sizes[i]); ptrs[i] = bufs[i].data(); }
+  emit_dumps(g, n_parts, ptrs.data());
+  for (int i = 0; i < n_parts; ++i) {
+    FILE* f = std::fopen(dump_paths[i], "wb");
+    if (!f) return fail(SHN_ERR_IO, "cannot create %s", dump_paths[i]);
+    const size_t put = std::fwrite(bufs[i].data(), 1, bufs[i].size(), f);
+    if (std::fclose(f) != 0 || put != bufs[i].size()) return fail(SHN_ERR_IO, "short write on %s", dump_paths[i]);
+  }
+  return SHN_OK;
+}
+
+int shn_dump_repartition(const void* const* dumps, const uint64_t* sizes, int n_parts_in, uint32_t dim, uint32_t m,
+                         int n_parts_out, void* const* out_dumps, uint64_t* out_sizes) {
+  if (!dumps || !sizes || !out_sizes || n_parts_in < 1 || n_parts_out < 1 || n_parts_out > 65535 || dim == 0 || m == 0 || m > 32)
+    return fail(SHN_ERR_ARG, "bad arguments");
+  HostGraph g;
+  std::string err;
+  if (!parse_dumps(dumps, sizes, n_parts_in, dim, m, g, err)) return fail(SHN_ERR_IO, "%s", err.c_str());
+  dump_sizes(g, n_parts_out, out_sizes);
+  if (out_dumps) emit_dumps(g, n_parts_out, out_dumps);
+  return SHN_OK;
+}
+
+void shn_index_free(shn_index* ix) {
+  if (!ix) return;
+  cudaSetDevice(ix->gpu);
+  if (ix->stream) cudaStreamSynchronize(ix->stream);
+  cudaFree(ix->d_vec); cudaFree(ix->d_l0); cudaFree(ix->d_up_base); cudaFree(ix->d_up); cudaFree(ix->d_ext_id);
+  cudaFree(ix->d_level);
+  cudaFree(ix->ws.counter); cudaFree(ix->ws.totals);
+  ix->ovf.release(); ix->q_stage.release(); ix->dist_stage.release(); ix->id_stage.release();
+  for (auto& e : ix->ev) if (e) cudaEventDestroy(e);
+  if (ix->stream) cudaStreamDestroy(ix->stream);
+  delete ix;
+}
+
+uint64_t shn_index_size(const shn_index* ix) { return ix ? ix->n : 0; }
+uint32_t shn_index_dim(const shn_index* ix) { return ix ? ix->dim : 0; }
+uint32_t shn_index_m(const shn_index* ix) { return ix ? ix->m : 0; }
+uint32_t shn_index_max_level(const shn_index* ix) { return ix ? ix->max_level : 0; }
+uint64_t shn_index_hbm_bytes(const shn_index* ix) { return ix ? ix->hbm_bytes : 0; }
+uint64_t shn_index_dump_bytes(const shn_index* ix) { return ix ? ix->dump_bytes : 0; }
+
+int shn_set_option(shn_index* ix, const char* key, int64_t value) {
+  if (!ix || !key) return fail(SHN_ERR_ARG, "null argument");
+  if (std::strcmp(key, "warps_per_sm") == 0) {
+    if (value < 0 || value > 64) return fail(SHN_ERR_ARG, "warps_per_sm must be in [0, 64]");
+    ix->warps_per_sm = static_cast<int>(value);
+    return SHN_OK;
+  }
+  return fail(SHN_ERR_ARG, "unknown option '%s'", key);
+}
+
+int shn_search_device(shn_index* ix, const float* d_queries, uint64_t nq, uint32_t k, uint32_t ef, uint32_t* d_out_ids,
+                      float* d_out_dists, uint32_t* d_per_query_counters, void* stream, shn_stats* stats) {
+  int rc = check_search_args(ix, nq, k, ef);
+  if (rc != SHN_OK) return rc;
+  if (stats) std::memset(stats, 0, sizeof *stats);
+  if (nq == 0) return SHN_OK;
+  if (!d_queries || !d_out_ids) return fail(SHN_ERR_ARG, "null buffer");
+  CU(cudaSetDevice(ix->gpu));
+  cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ix->stream;
+  rc = run_search(ix, d_queries, nq, k, ef, d_out_ids, d_out_dists, d_per_query_counters, s, stats != nullptr);
+  if (rc != SHN_OK) return rc;
+  if (stats) {
+    unsigned long long t[kNumTotals];
+    CU(cudaMemcpyAsync(t, ix->ws.totals, sizeof t, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, ix->ev[1], ix->ev[2]));
+    fill_stats(ix, t, nq, stats);
+    stats->kernel_ms = ms;
+    if (t[kFailedQueries]) return fail(SHN_ERR_CAPACITY, "%llu queries overflowed the visited set (ef=%u)", t[kFailedQueries], ef);
+  }
+  return SHN_OK;
+}
+
+int shn_search(shn_index* ix, const float* queries, uint64_t nq, uint32_t k, uint32_t ef, uint32_t* out_ids,
+               float* out_dists, shn_stats* stats) {
+  int rc = check_search_args(ix, nq, k, ef);
+  if (rc != SHN_OK) return rc;
+  if (stats) std::memset(stats, 0, sizeof *stats);
+  if (nq == 0) return SHN_OK;
+  if (!queries || !out_ids) return fail(SHN_ERR_ARG, "null buffer");
+  CU(cudaSetDevice(ix->gpu));
+  if (ix->q_stage.ensure(nq * ix->dim) != cudaSuccess || ix->id_stage.ensure(nq * k) != cudaSuccess ||
+      ix->dist_stage.ensure(nq * k) != cudaSuccess)
+    return fail(SHN_ERR_CUDA, "cannot allocate staging buffers for %llu queries", static_cast<unsigned long long>(nq));
+  cudaStream_t s = ix->stream;
+  CU(cudaEventRecord(ix->ev[0], s));
+  CU(cudaMemcpyAsync(ix->q_stage.p, queries, nq * ix->dim * sizeof(float), cudaMemcpyHostToDevice, s));
+  rc = run_search(ix, ix->q_stage.p, nq, k, ef, ix->id_stage.p, ix->dist_stage.p, nullptr, s, true);
+  if (rc != SHN_OK) return rc;
+  CU(cudaMemcpyAsync(out_ids, ix->id_stage.p, nq * k * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+  if (out_dists) CU(cudaMemcpyAsync(out_dists, ix->dist_stage.p, nq * k * sizeof(float), cudaMemcpyDeviceToHost, s));
+  unsigned long long t[kNumTotals];
+  CU(cudaMemcpyAsync(t, ix->ws.totals, sizeof t, cudaMemcpyDeviceToHost, s));
+  CU(cudaEventRecord(ix->ev[3], s));
+  CU(cudaStreamSynchronize(s));
+  if (stats) {
+    float h2d = 0.f, ker = 0.f, d2h = 0.f;
+    CU(cudaEventElapsedTime(&h2d, ix->ev[0], ix->ev[1]));
+    CU(cudaEventElapsedTime(&ker, ix->ev[1], ix->ev[2]));
+    CU(cudaEventElapsedTime(&d2h, ix->ev[2], ix->ev[3]));
+    fill_stats(ix, t, nq, stats);
+    stats->kernel_ms = ker; stats->h2d_ms = h2d; stats->d2h_ms = d2h;
+  }
+  if (t[kFailedQueries]) return fail(SHN_ERR_CAPACITY, "%llu queries overflowed the visited set (ef=%u)", t[kFailedQueries], ef);
+  return SHN_OK;
+}
+
+const char* shn_last_error(void) { return g_err.c_str(); }
+const char* shn_version(void) { return "shn_b200 0.1 (sm_100a)"; }
+
+}  // extern "C"

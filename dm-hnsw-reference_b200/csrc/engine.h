@@ -1,0 +1,45 @@
+// engine.h — internal C++ interface between the C ABI (capi.cu) and the CUDA kernels.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "graph.h"
+
+namespace shn {
+
+// Indices into the device-side totals array (u64 each), summed over the queries of one launch.
+enum Total { kDistcomps = 0, kVisitedUpper, kVisitedL0, kListsL0, kListsUpper, kOverflowQueries, kFailedQueries, kNumTotals };
+
+// Per-query counter record written when the caller asks for it (shn_search_device per_query_counters).
+constexpr int kPerQueryWords = 6;  // distcomps, visited_nodes, visited_nodes_l0, lists_l0, lists_upper, overflow
+
+struct SearchWorkspace {
+  uint32_t* counter = nullptr;            // work cursor
+  unsigned long long* totals = nullptr;   // [kNumTotals]
+  uint32_t* ovf = nullptr;                // [ovf_slots][ovf_cap], all kInvalid at rest
+  uint32_t ovf_cap = 0, ovf_slots = 0;
+};
+
+struct SearchConfig {
+  uint32_t k, ef;
+  bool ip;
+  int warps_per_sm;  // 0 = auto
+  int num_sms;
+};
+
+// Number of warp slots the launch will use (so the caller can size the overflow tables), given k/ef/dim.
+cudaError_t search_plan(const DeviceGraph& g, const SearchConfig& cfg, uint32_t nq, int* grid, int* block, size_t* smem,
+                        uint32_t* vis_cap);
+
+// Enqueue the search of nq queries on `stream`.  d_per_query may be null.  ws.totals/ws.counter are reset on the
+// stream first.  No synchronisation.
+cudaError_t search_launch(const DeviceGraph& g, const SearchConfig& cfg, const float* d_queries, uint32_t nq,
+                          uint32_t* d_ids, float* d_dists, uint32_t* d_per_query, SearchWorkspace& ws,
+                          cudaStream_t stream);
+
+// Exact top-k by brute force over base[n][dim] (row stride = dim floats): ids are row numbers.
+cudaError_t bruteforce_launch(const float* d_base, uint64_t n, const float* d_queries, uint32_t nq, uint32_t dim, bool ip,
+                              uint32_t k, uint32_t* d_ids, float* d_dists, cudaStream_t stream);
+
+}  // namespace shn

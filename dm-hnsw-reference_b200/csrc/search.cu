@@ -1,0 +1,291 @@
+// search.cu — batched k-NN search: one warp per query, persistent warps pulling queries from a global cursor.
+//
+// Restates HNSW::knn (src/hnsw/hnsw.hh:253-307): entry point -> greedy descent through the upper layers
+// (search_for_one<without_lock>, :332-393) -> ef-bounded best-first search on layer 0
+// (search_level<without_lock>, :407-476) -> trim to k (:296-298).  What the reference does with one RDMA READ per
+// neighbour and a coroutine switch (src/rdma/rdma_reads.hh:9,40) is here a wave of 128-bit loads from HBM.
+// Semantics kept exactly: neighbours are admitted in stored list order against the running
+// farthest distance, strict '<', visited marked before the distance is computed; distances are summed in the
+// reference's own order (search.cuh), so ids and distances are bit-identical except on exact distance ties.
+#include <cstdio>
+
+#include "engine.h"
+#include "search.cuh"
+
+namespace shn {
+namespace {
+
+constexpr int kWarpsPerBlock = 4;
+
+struct SearchParams {
+  DeviceGraph g;
+  const float* queries;
+  uint32_t nq, k, ef;
+  uint32_t* out_ids;
+  float* out_dists;
+  uint32_t* per_query;
+  uint32_t* counter;
+  unsigned long long* totals;
+  uint32_t* ovf;
+  uint32_t vis_cap, vis_limit, ovf_cap, ovf_limit;
+  uint32_t q_floats, ef_cap;  // shared-memory strides
+};
+
+__host__ __device__ inline size_t warp_smem_bytes(uint32_t q_floats, uint32_t ef_cap, uint32_t vis_cap) {
+  return 4ull * (q_floats + 2 * ef_cap + 2 * kMaxList + vis_cap);
+}
+
+template <bool IP, int NCHUNK>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) search_kernel(const SearchParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const DeviceGraph& g = p.g;
+
+  unsigned char* base = smem_raw + warp * warp_smem_bytes(p.q_floats, p.ef_cap, p.vis_cap);
+  float* s_q = reinterpret_cast<float*>(base);
+  float* qd = s_q + p.q_floats;
+  uint32_t* qi = reinterpret_cast<uint32_t*>(qd + p.ef_cap);
+  uint32_t* s_rows = qi + p.ef_cap;
+  float* s_dist = reinterpret_cast<float*>(s_rows + kMaxList);
+  VisitedSet vis;
+  vis.tab = reinterpret_cast<uint32_t*>(s_dist + kMaxList);
+  vis.cap = p.vis_cap; vis.limit = p.vis_limit;
+  vis.ovf = p.ovf + static_cast<size_t>(blockIdx.x * kWarpsPerBlock + warp) * p.ovf_cap;
+  vis.ovf_cap = p.ovf_cap; vis.ovf_limit = p.ovf_limit;
+  vis.count = 0; vis.ovf_count = 0; vis.failed = false;
+
+  unsigned long long t_dist = 0, t_vup = 0, t_vl0 = 0, t_l0 = 0, t_lup = 0, t_ovf = 0, t_fail = 0;
+  const uint32_t m = g.m, m0 = g.m0, ef = p.ef;
+
+  for (;;) {
+    uint32_t q = 0;
+    if (lane == 0) q = atomicAdd(p.counter, 1u);
+    q = __shfl_sync(kFull, q, 0);
+    if (q >= p.nq) break;
+
+    // stage the query (database slot components, io/database.hh:17-21)
+    const float* gq = p.queries + static_cast<size_t>(q) * g.dim;
+    for (uint32_t j = lane; j < p.q_floats; j += 32) s_q[j] = j < g.dim ? __ldg(gq + j) : 0.f;
+    visited_reset(vis, lane);
+
+    uint32_t c_dist = 0, c_vup = 0, c_vl0 = 0, c_l0 = 0, c_lup = 0;
+
+    // hnsw.hh:261-272 — the entry point and its distance
+    uint32_t cur = g.ep_row;
+    if (g.ep_level > 0) ++c_vup; else ++c_vl0;
+    if (lane == 0) s_rows[0] = cur;
+    __syncwarp();
+    eval_rows<IP, NCHUNK>(g, s_q, s_rows, 1, s_dist, lane);
+    float closest = s_dist[0];
+    ++c_dist;
+    __syncwarp();
+
+    // search_for_one<without_lock>: levels ep.level .. 1 (hnsw.hh:341-391)
+    for (uint32_t level = g.ep_level; level > 0; --level) {
+      bool changed = true;
+      while (changed) {
+        changed = false;
+        const uint32_t* list = g.up + (static_cast<size_t>(__ldg(g.up_base + cur)) + (level - 1)) * m;
+        ++c_lup;
+        const uint32_t nb = lane < m ? __ldg(list + lane) : kInvalid;
+        const uint32_t valid = __ballot_sync(kFull, nb != kInvalid);  // lists are stored compacted
+        const uint32_t cnt = __popc(valid);
+        if (nb != kInvalid) s_rows[lane] = nb;
+        __syncwarp();
+        if (cnt == 0) break;
+        eval_rows<IP, NCHUNK>(g, s_q, s_rows, cnt, s_dist, lane);
+        c_vup += cnt; c_dist += cnt;
+        // sequential scan with strict '<' (hnsw.hh:378-382) == first index of the list minimum, if it beats closest
+        float bd = lane < cnt ? s_dist[lane] : __int_as_float(0x7f800000);
+        uint32_t bi = lane;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const float od = __shfl_xor_sync(kFull, bd, o);
+          const uint32_t oi = __shfl_xor_sync(kFull, bi, o);
+          if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
+        }
+        if (bi < cnt && bd < closest) {
+          closest = bd;
+          cur = s_rows[bi];
+          changed = true;
+        }
+        __syncwarp();
+      }
+    }
+
+    // hnsw.hh:285-288 — distance recomputed (same bits), seed of the level-0 search
+    ++c_dist;
+    uint32_t qsize = 0;
+    if (lane == 0) { qd[0] = closest; qi[0] = cur; }
+    qsize = 1;
+    visited_test_and_set(vis, cur, lane == 0, lane);
+    uint32_t lb = 0;  // every entry below lb is expanded
+
+    // search_level<without_lock>(ef, level 0) (hnsw.hh:417-473)
+    for (;;) {
+      // next_candidates.pop(): the closest entry not yet expanded
+      uint32_t pos = kInvalid;
+      for (uint32_t b = lb & ~31u; b < qsize; b += 32) {
+        const uint32_t j = b + lane;
+        const bool un = j < qsize && j >= lb && !(qi[j] & kExpanded);
+        const uint32_t mask = __ballot_sync(kFull, un);
+        if (mask) { pos = b + __ffs(mask) - 1; break; }
+      }
+      if (pos == kInvalid) break;  // what is left of next_candidates is farther than top_candidates.top() (:424)
+      const uint32_t cand = qi[pos];
+      __syncwarp();
+      if (lane == 0) qi[pos] = cand | kExpanded;
+      lb = pos + 1;
+      ++c_l0;
+
+      // read_neighborlist + the visited filter, in stored order (:437-443)
+      uint32_t cnt = 0;
+      for (uint32_t j0 = 0; j0 < m0; j0 += 32) {
+        const uint32_t j = j0 + lane;
+        const uint32_t nb = j < m0 ? __ldg(g.l0 + static_cast<size_t>(cand) * m0 + j) : kInvalid;
+        const bool fresh = visited_test_and_set(vis, nb, nb != kInvalid, lane);
+        const uint32_t mask = __ballot_sync(kFull, fresh);
+        if (fresh) s_rows[cnt + __popc(mask & ((1u << lane) - 1))] = nb;
+        cnt += __popc(mask);
+      }
+      __syncwarp();
+      if (cnt == 0) continue;
+      c_vl0 += cnt; c_dist += cnt;
+      eval_rows<IP, NCHUNK>(g, s_q, s_rows, cnt, s_dist, lane);
+
+      // admission in list order against the running farthest distance (:456-465, heap.hh:34-41)
+      for (uint32_t i = 0; i < cnt; ++i) {
+        const float d = s_dist[i];
+        if (qsize < ef || d < qd[ef - 1]) {
+          const uint32_t at = queue_insert(qd, qi, qsize, ef, d, s_rows[i], lane);
+          if (at < lb) lb = at;
+        }
+      }
+    }
+
+    // trim to k (:296-298); the reference reports ids in heap-array order, here ascending by distance
+    for (uint32_t j = lane; j < p.k; j += 32) {
+      const bool ok = j < qsize;
+      p.out_ids[static_cast<size_t>(q) * p.k + j] = ok ? __ldg(g.ext_id + (qi[j] & ~kExpanded)) : kInvalid;
+      if (p.out_dists) p.out_dists[static_cast<size_t>(q) * p.k + j] = ok ? qd[j] : __int_as_float(0x7f800000);
+    }
+    const uint32_t overflowed = vis.ovf_count ? 1u : 0u;
+    if (p.per_query && lane == 0) {
+      uint32_t* o = p.per_query + static_cast<size_t>(q) * kPerQueryWords;
+      o[0] = c_dist; o[1] = c_vup; o[2] = c_vl0; o[3] = c_l0; o[4] = c_lup; o[5] = overflowed | (vis.failed ? 2u : 0u);
+    }
+    t_dist += c_dist; t_vup += c_vup; t_vl0 += c_vl0; t_l0 += c_l0; t_lup += c_lup; t_ovf += overflowed;
+    t_fail += vis.failed ? 1u : 0u;
+    __syncwarp();
+  }
+
+  if (vis.ovf_count) visited_reset(vis, lane);  // leave the HBM table clean for the next launch
+  if (lane == 0) {
+    atomicAdd(p.totals + kDistcomps, t_dist);
+    atomicAdd(p.totals + kVisitedUpper, t_vup);
+    atomicAdd(p.totals + kVisitedL0, t_vl0);
+    atomicAdd(p.totals + kListsL0, t_l0);
+    atomicAdd(p.totals + kListsUpper, t_lup);
+    if (t_ovf) atomicAdd(p.totals + kOverflowQueries, t_ovf);
+    if (t_fail) atomicAdd(p.totals + kFailedQueries, t_fail);
+  }
+}
+
+uint32_t next_pow2(uint32_t v) {
+  uint32_t p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+// Shared visited table: sized for the typical query (about 20 x ef nodes are touched at m = 16), the tail spills.
+uint32_t pick_vis_cap(uint32_t ef, uint32_t m0) {
+  const uint32_t want = ef * (m0 > 32 ? 40u : 24u);
+  uint32_t cap = next_pow2(want);
+  if (cap < 1024) cap = 1024;
+  if (cap > 16384) cap = 16384;
+  return cap;
+}
+
+template <bool IP, int NCHUNK>
+cudaError_t launch_t(const SearchParams& p, int grid, size_t smem, cudaStream_t stream) {
+  cudaError_t e = cudaFuncSetAttribute(search_kernel<IP, NCHUNK>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  if (e != cudaSuccess) return e;
+  search_kernel<IP, NCHUNK><<<grid, kWarpsPerBlock * 32, smem, stream>>>(p);
+  return cudaGetLastError();
+}
+
+template <bool IP, int NCHUNK>
+cudaError_t occupancy_t(size_t smem, int* blocks) {
+  cudaError_t e = cudaFuncSetAttribute(search_kernel<IP, NCHUNK>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  if (e != cudaSuccess) return e;
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, search_kernel<IP, NCHUNK>, kWarpsPerBlock * 32, smem);
+}
+
+int chunk_variant(uint32_t dim) { return dim == 128 ? 8 : (dim == 96 ? 6 : 0); }
+
+}  // namespace
+
+cudaError_t search_plan(const DeviceGraph& g, const SearchConfig& cfg, uint32_t nq, int* grid, int* block, size_t* smem,
+                        uint32_t* vis_cap_out) {
+  const uint32_t q_floats = g.row_f4 * 4;
+  const uint32_t ef_cap = (cfg.ef + 31u) & ~31u;
+  uint32_t vis_cap = pick_vis_cap(cfg.ef, g.m0);
+  size_t bytes = kWarpsPerBlock * warp_smem_bytes(q_floats, ef_cap, vis_cap);
+  while (bytes > 200 * 1024 && vis_cap > 1024) {
+    vis_cap >>= 1;
+    bytes = kWarpsPerBlock * warp_smem_bytes(q_floats, ef_cap, vis_cap);
+  }
+  if (bytes > 227 * 1024) return cudaErrorInvalidValue;
+  int blocks = 0;
+  cudaError_t e;
+  const int v = chunk_variant(g.dim);
+  if (cfg.ip) e = v == 8 ? occupancy_t<true, 8>(bytes, &blocks) : v == 6 ? occupancy_t<true, 6>(bytes, &blocks) : occupancy_t<true, 0>(bytes, &blocks);
+  else        e = v == 8 ? occupancy_t<false, 8>(bytes, &blocks) : v == 6 ? occupancy_t<false, 6>(bytes, &blocks) : occupancy_t<false, 0>(bytes, &blocks);
+  if (e != cudaSuccess) return e;
+  if (blocks < 1) return cudaErrorInvalidConfiguration;
+  if (cfg.warps_per_sm > 0) {
+    const int want = (cfg.warps_per_sm + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    if (want < blocks) blocks = want;
+  }
+  long long gsz = static_cast<long long>(blocks) * cfg.num_sms;
+  const long long need = (static_cast<long long>(nq) + kWarpsPerBlock - 1) / kWarpsPerBlock;
+  if (gsz > need) gsz = need;
+  if (gsz < 1) gsz = 1;
+  *grid = static_cast<int>(gsz);
+  *block = kWarpsPerBlock * 32;
+  *smem = bytes;
+  *vis_cap_out = vis_cap;
+  return cudaSuccess;
+}
+
+cudaError_t search_launch(const DeviceGraph& g, const SearchConfig& cfg, const float* d_queries, uint32_t nq,
+                          uint32_t* d_ids, float* d_dists, uint32_t* d_per_query, SearchWorkspace& ws,
+                          cudaStream_t stream) {
+  int grid, block;
+  size_t smem;
+  uint32_t vis_cap;
+  cudaError_t e = search_plan(g, cfg, nq, &grid, &block, &smem, &vis_cap);
+  if (e != cudaSuccess) return e;
+  if (static_cast<uint32_t>(grid) * kWarpsPerBlock > ws.ovf_slots) return cudaErrorInvalidValue;
+
+  SearchParams p;
+  p.g = g;
+  p.queries = d_queries; p.nq = nq; p.k = cfg.k; p.ef = cfg.ef;
+  p.out_ids = d_ids; p.out_dists = d_dists; p.per_query = d_per_query;
+  p.counter = ws.counter; p.totals = ws.totals; p.ovf = ws.ovf;
+  p.vis_cap = vis_cap; p.vis_limit = vis_cap / 4 * 3;
+  p.ovf_cap = ws.ovf_cap; p.ovf_limit = ws.ovf_cap / 4 * 3;
+  p.q_floats = g.row_f4 * 4; p.ef_cap = (cfg.ef + 31u) & ~31u;
+
+  e = cudaMemsetAsync(ws.counter, 0, sizeof(uint32_t), stream);
+  if (e != cudaSuccess) return e;
+  e = cudaMemsetAsync(ws.totals, 0, kNumTotals * sizeof(unsigned long long), stream);
+  if (e != cudaSuccess) return e;
+
+  const int v = chunk_variant(g.dim);
+  if (cfg.ip) return v == 8 ? launch_t<true, 8>(p, grid, smem, stream) : v == 6 ? launch_t<true, 6>(p, grid, smem, stream) : launch_t<true, 0>(p, grid, smem, stream);
+  return v == 8 ? launch_t<false, 8>(p, grid, smem, stream) : v == 6 ? launch_t<false, 6>(p, grid, smem, stream) : launch_t<false, 0>(p, grid, smem, stream);
+}
+
+}  // namespace shn

@@ -21,170 +21,115 @@ constexpr int kMaxList = 64;                  // 2m <= 64
 __device__ __forceinline__ float4 ldg_f4(const float4* p) { return __ldg(p); }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Distances.
-//
-// FAST: lane l owns float4 #(l + 32 t) of the row; partial sums are combined across the warp.  For a batch of
-// U rows the U partials per lane are reduced with a halving exchange (U/2 + U/4 + ... shuffles instead of 5 U).
-// EXACT: reproduces the reference's summation order bit for bit (see oracle/hnsw_oracle.c): a lane pair owns one
-// row, lane h of the pair accumulates AVX lanes 4h..4h+3 of the reference's 8-lane loop.
+// Distances, in the reference's summation order (bit-identical results; see oracle/hnsw_oracle.c for how the
+// order was read off the reference build).  The reference accumulates 8 AVX lanes j over 16-element chunks c:
+//   L2:  S_j += fma(d0_j, d0_j, d1_j * d1_j)      d0 = q[16c+j] - v[16c+j],  d1 = q[16c+8+j] - v[16c+8+j]
+//   IP:  S_j += fma(q[16c+j], v[16c+j], q[16c+8+j] * v[16c+8+j])
+// A lane PAIR owns one row: lane h of the pair carries S_{4h..4h+3} and reads the 16-byte pieces
+// {16c+4h.., 16c+8+4h..} of every chunk, so the pair's two loads cover one 32-byte sector each and a warp
+// evaluates 16 rows per pass with up to 8 independent 128-bit loads in flight per lane.
 // ---------------------------------------------------------------------------------------------------------------
 
 template <bool IP>
-__device__ __forceinline__ float fast_partial(const float4& q, const float4& v, float acc) {
+__device__ __forceinline__ void chunk_accumulate(const float4& qa, const float4& qb, const float4& a, const float4& b,
+                                                 float& s0, float& s1, float& s2, float& s3) {
   if (IP) {
-    acc = fmaf(q.x, v.x, acc); acc = fmaf(q.y, v.y, acc); acc = fmaf(q.z, v.z, acc); acc = fmaf(q.w, v.w, acc);
+    s0 = __fadd_rn(s0, __fmaf_rn(qa.x, a.x, __fmul_rn(qb.x, b.x)));
+    s1 = __fadd_rn(s1, __fmaf_rn(qa.y, a.y, __fmul_rn(qb.y, b.y)));
+    s2 = __fadd_rn(s2, __fmaf_rn(qa.z, a.z, __fmul_rn(qb.z, b.z)));
+    s3 = __fadd_rn(s3, __fmaf_rn(qa.w, a.w, __fmul_rn(qb.w, b.w)));
   } else {
-    float d;
-    d = q.x - v.x; acc = fmaf(d, d, acc);
-    d = q.y - v.y; acc = fmaf(d, d, acc);
-    d = q.z - v.z; acc = fmaf(d, d, acc);
-    d = q.w - v.w; acc = fmaf(d, d, acc);
+    float d0, d1;
+    d0 = __fsub_rn(qa.x, a.x); d1 = __fsub_rn(qb.x, b.x); s0 = __fadd_rn(s0, __fmaf_rn(d0, d0, __fmul_rn(d1, d1)));
+    d0 = __fsub_rn(qa.y, a.y); d1 = __fsub_rn(qb.y, b.y); s1 = __fadd_rn(s1, __fmaf_rn(d0, d0, __fmul_rn(d1, d1)));
+    d0 = __fsub_rn(qa.z, a.z); d1 = __fsub_rn(qb.z, b.z); s2 = __fadd_rn(s2, __fmaf_rn(d0, d0, __fmul_rn(d1, d1)));
+    d0 = __fsub_rn(qa.w, a.w); d1 = __fsub_rn(qb.w, b.w); s3 = __fadd_rn(s3, __fmaf_rn(d0, d0, __fmul_rn(d1, d1)));
   }
-  return acc;
 }
 
-__device__ __forceinline__ float warp_sum(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
-  return v;
-}
-
-// Reduce U (power of two, <= 8) per-lane partials across the warp.  Afterwards value index
-// idx(lane) = bits of lane above log2(32/U) (see code) is complete in every lane of its group.
-template <int U>
-__device__ __forceinline__ float multi_reduce(float (&p)[U], int lane, int& owner_idx) {
-  int idx = 0;
-  int width = U;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    if (width > 1) {
-      const int half = width / 2;
-      const bool upper = (lane & o) != 0;
-#pragma unroll
-      for (int i = 0; i < half; ++i) {
-        const float send = upper ? p[i] : p[i + half];
-        const float keep = upper ? p[i + half] : p[i];
-        p[i] = keep + __shfl_xor_sync(kFull, send, o);
-      }
-      idx = idx * 2 + (upper ? 1 : 0);
-      width = half;
-    } else {
-      p[0] += __shfl_xor_sync(kFull, p[0], o);
-    }
-  }
-  // idx was built most-significant-first over the halving rounds, but value i of round r came from p[i + half]
-  // for the upper lanes: the surviving value index is sum(upper_r * half_r).
-  owner_idx = idx;
-  return p[0];
-}
-
-// Evaluate dist(query, row) for rows s_rows[0..cnt) -> s_out[0..cnt).  FAST path.
-// qreg: the query as NV float4 per lane (float4 #(lane + 32 t)), zero beyond dim.
-template <int NV, bool IP>
-__device__ __forceinline__ void eval_rows_fast(const DeviceGraph& g, const float4 (&qreg)[NV], const uint32_t* s_rows,
-                                               uint32_t cnt, float* s_out, int lane) {
-  constexpr int U = NV == 1 ? 8 : (NV == 2 ? 4 : 2);
-  const uint32_t dim4 = g.row_f4;
-  for (uint32_t base = 0; base < cnt; base += U) {
-    float4 v[U][NV];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const uint32_t i = base + u;
-      const uint32_t row = s_rows[i < cnt ? i : cnt - 1];  // clamp: redundant load instead of a branch
-      const float4* rp = g.vec + static_cast<size_t>(row) * dim4;
-#pragma unroll
-      for (int t = 0; t < NV; ++t) {
-        const uint32_t f = lane + 32 * t;
-        v[u][t] = (NV * 32 == dim4 || f < dim4) ? ldg_f4(rp + f) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-    }
-    float p[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      float acc = 0.f;
-#pragma unroll
-      for (int t = 0; t < NV; ++t) acc = fast_partial<IP>(qreg[t], v[u][t], acc);
-      p[u] = acc;
-    }
-    int idx;
-    float r = multi_reduce<U>(p, lane, idx);
-    if (IP) r = 1.0f - r;
-    constexpr int group = 32 / U;  // lanes sharing one value
-    if ((lane & (group - 1)) == 0 && base + idx < cnt) s_out[base + idx] = r;
-  }
-  __syncwarp();
-}
-
-// EXACT path: s_q = query in shared memory (dim floats, 16-byte aligned).
+// Horizontal step + scalar tail (distance.hh:40,112-115 / :134-139), both lanes of the pair get the result.
 template <bool IP>
-__device__ __forceinline__ void eval_rows_exact(const DeviceGraph& g, const float* s_q, const uint32_t* s_rows,
-                                                uint32_t cnt, float* s_out, int lane) {
-  const uint32_t dim = g.dim;
-  const uint32_t nchunk = dim >> 4;  // distance.hh:88 qty16
+__device__ __forceinline__ float finish_row(float s0, float s1, float s2, float s3, int h, const float* s_q,
+                                            const float* row, uint32_t dim) {
+  const uint32_t d16 = dim & ~15u;
+  float r;
+  if (IP) {
+    // r = ((1 - (S4+S5)) - ((S0+S1)+(S2+S3))) - (S6+S7);  tail: t += q*v; r -= t
+    const float t01 = __fadd_rn(s0, s1), t23 = __fadd_rn(s2, s3);
+    const float p01 = __shfl_xor_sync(kFull, t01, 1), p23 = __shfl_xor_sync(kFull, t23, 1);
+    const float A = h ? __fadd_rn(p01, p23) : __fadd_rn(t01, t23);
+    const float B = h ? t01 : p01;
+    const float C = h ? t23 : p23;
+    r = __fsub_rn(__fsub_rn(__fsub_rn(1.0f, B), A), C);
+    if (dim & 15u) {
+      float t = 0.f;
+      for (uint32_t e = d16; e < dim; ++e) t = __fadd_rn(t, __fmul_rn(s_q[e], __ldg(row + e)));
+      r = __fsub_rn(r, t);
+    }
+  } else {
+    // x_j = S_j + S_{j+4};  r = (x1 + x3) + (x0 + x2);  tail: r += (q-v)^2
+    const float x0 = __fadd_rn(s0, __shfl_xor_sync(kFull, s0, 1));
+    const float x1 = __fadd_rn(s1, __shfl_xor_sync(kFull, s1, 1));
+    const float x2 = __fadd_rn(s2, __shfl_xor_sync(kFull, s2, 1));
+    const float x3 = __fadd_rn(s3, __shfl_xor_sync(kFull, s3, 1));
+    r = __fadd_rn(__fadd_rn(x1, x3), __fadd_rn(x0, x2));
+    for (uint32_t e = d16; e < dim; ++e) {
+      const float d = __fsub_rn(s_q[e], __ldg(row + e));
+      r = __fadd_rn(r, __fmul_rn(d, d));
+    }
+  }
+  return r;
+}
+
+// dist(query, row) for rows s_rows[0..cnt) -> s_out[0..cnt).  s_q: the query in shared memory (16-byte aligned,
+// dim floats).  NCHUNK > 0: dim == 16*NCHUNK known at compile time (fully unrolled, all loads of a pass in flight);
+// NCHUNK == 0: any dim.
+template <bool IP, int NCHUNK>
+__device__ __forceinline__ void eval_rows(const DeviceGraph& g, const float* s_q, const uint32_t* s_rows, uint32_t cnt,
+                                          float* s_out, int lane) {
   const int h = lane & 1;
   const float4* s_q4 = reinterpret_cast<const float4*>(s_q);
   for (uint32_t base = 0; base < cnt; base += 16) {
     const uint32_t i = base + (lane >> 1);
-    const uint32_t row = s_rows[i < cnt ? i : cnt - 1];
+    const uint32_t row = s_rows[i < cnt ? i : cnt - 1];  // clamp: a redundant load instead of a divergent branch
     const float4* rp = g.vec + static_cast<size_t>(row) * g.row_f4;
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;  // AVX lanes 4h .. 4h+3
-    for (uint32_t c0 = 0; c0 < nchunk; c0 += 4) {
-      float4 a[4], b[4];
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    if (NCHUNK > 0) {
+      constexpr int NC = NCHUNK > 0 ? NCHUNK : 1;
+      constexpr int STEP = NC < 8 ? NC : 8;  // chunks per wave of loads (2 loads each)
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        if (c0 + c < nchunk) {
-          a[c] = ldg_f4(rp + (c0 + c) * 4 + h);      // elements 16c + 4h ..      (first 8 of the 16)
-          b[c] = ldg_f4(rp + (c0 + c) * 4 + 2 + h);  // elements 16c + 8 + 4h ..  (second 8)
-        }
-      }
+      for (int c0 = 0; c0 < NC; c0 += STEP) {
+        float4 a[STEP], b[STEP];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        if (c0 + c < nchunk) {
-          const float4 qa = s_q4[(c0 + c) * 4 + h];
-          const float4 qb = s_q4[(c0 + c) * 4 + 2 + h];
-          if (IP) {  // s_j += fma(a_j, b_j, a_{8+j} * b_{8+j})   (query is the first operand, hnsw.hh:271,375,458)
-            s0 = __fadd_rn(s0, __fmaf_rn(qa.x, a[c].x, __fmul_rn(qb.x, b[c].x)));
-            s1 = __fadd_rn(s1, __fmaf_rn(qa.y, a[c].y, __fmul_rn(qb.y, b[c].y)));
-            s2 = __fadd_rn(s2, __fmaf_rn(qa.z, a[c].z, __fmul_rn(qb.z, b[c].z)));
-            s3 = __fadd_rn(s3, __fmaf_rn(qa.w, a[c].w, __fmul_rn(qb.w, b[c].w)));
-          } else {   // s_j += fma(d0_j, d0_j, d1_j * d1_j)
-            float d0, d1;
-            d0 = __fsub_rn(qa.x, a[c].x); d1 = __fsub_rn(qb.x, b[c].x); s0 = __fadd_rn(s0, __fmaf_rn(d0, d0, __fmul_rn(d1, d1)));
-            d0 = __fsub_rn(qa.y, a[c].y); d1 = __fsub_rn(qb.y, b[c].y); s1 = __fadd_rn(s1, __fmaf_rn(d0, d0, __fmul_rn(d1, d1)));
-            d0 = __fsub_rn(qa.z, a[c].z); d1 = __fsub_rn(qb.z, b[c].z); s2 = __fadd_rn(s2, __fmaf_rn(d0, d0, __fmul_rn(d1, d1)));
-            d0 = __fsub_rn(qa.w, a[c].w); d1 = __fsub_rn(qb.w, b[c].w); s3 = __fadd_rn(s3, __fmaf_rn(d0, d0, __fmul_rn(d1, d1)));
+        for (int c = 0; c < STEP; ++c) {
+          if (c0 + c < NC) {
+            a[c] = ldg_f4(rp + (c0 + c) * 4 + h);
+            b[c] = ldg_f4(rp + (c0 + c) * 4 + 2 + h);
           }
         }
-      }
-    }
-    float r;
-    if (IP) {
-      // r = ((1 - (S4+S5)) - ((S0+S1)+(S2+S3))) - (S6+S7)
-      const float t01 = __fadd_rn(s0, s1), t23 = __fadd_rn(s2, s3);
-      const float p01 = __shfl_xor_sync(kFull, t01, 1), p23 = __shfl_xor_sync(kFull, t23, 1);
-      const float A = h ? __fadd_rn(p01, p23) : __fadd_rn(t01, t23);
-      const float B = h ? t01 : p01;
-      const float C = h ? t23 : p23;
-      r = __fsub_rn(__fsub_rn(__fsub_rn(1.0f, B), A), C);
-      if (dim & 15u) {
-        float t = 0.f;
-        const float* rs = reinterpret_cast<const float*>(rp);
-        for (uint32_t e = nchunk * 16; e < dim; ++e) t = __fadd_rn(t, __fmul_rn(s_q[e], __ldg(rs + e)));
-        r = __fsub_rn(r, t);
+#pragma unroll
+        for (int c = 0; c < STEP; ++c) {
+          if (c0 + c < NC) chunk_accumulate<IP>(s_q4[(c0 + c) * 4 + h], s_q4[(c0 + c) * 4 + 2 + h], a[c], b[c], s0, s1, s2, s3);
+        }
       }
     } else {
-      // x_j = S_j + S_{j+4};  r = (x1 + x3) + (x0 + x2)
-      const float x0 = __fadd_rn(s0, __shfl_xor_sync(kFull, s0, 1));
-      const float x1 = __fadd_rn(s1, __shfl_xor_sync(kFull, s1, 1));
-      const float x2 = __fadd_rn(s2, __shfl_xor_sync(kFull, s2, 1));
-      const float x3 = __fadd_rn(s3, __shfl_xor_sync(kFull, s3, 1));
-      r = __fadd_rn(__fadd_rn(x1, x3), __fadd_rn(x0, x2));
-      const float* rs = reinterpret_cast<const float*>(rp);
-      for (uint32_t e = nchunk * 16; e < dim; ++e) {
-        const float d = __fsub_rn(s_q[e], __ldg(rs + e));
-        r = __fadd_rn(r, __fmul_rn(d, d));
+      const uint32_t nchunk = g.dim >> 4;
+      for (uint32_t c0 = 0; c0 < nchunk; c0 += 4) {
+        float4 a[4], b[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if (c0 + c < nchunk) {
+            a[c] = ldg_f4(rp + (c0 + c) * 4 + h);
+            b[c] = ldg_f4(rp + (c0 + c) * 4 + 2 + h);
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if (c0 + c < nchunk) chunk_accumulate<IP>(s_q4[(c0 + c) * 4 + h], s_q4[(c0 + c) * 4 + 2 + h], a[c], b[c], s0, s1, s2, s3);
+        }
       }
     }
+    const float r = finish_row<IP>(s0, s1, s2, s3, h, s_q, reinterpret_cast<const float*>(rp), g.dim);
     if (h == 0 && i < cnt) s_out[i] = r;
   }
   __syncwarp();
@@ -209,7 +154,7 @@ __device__ __forceinline__ uint32_t queue_insert(float* qd, uint32_t* qi, uint32
   }
   const uint32_t nsize = qsize < ef ? qsize + 1 : ef;
   if (pos >= nsize) return kInvalid;
-  int hi = static_cast<int>(nsize) - 1;  // source range is [pos, hi)
+  int hi = static_cast<int>(nsize) - 1;  // entries [pos, hi) move up by one, highest block first
   while (hi > static_cast<int>(pos)) {
     const int lo = max(static_cast<int>(pos), hi - 32);
     const int j = lo + lane;
@@ -241,7 +186,7 @@ struct VisitedSet {
   bool failed;
 };
 
-__device__ __forceinline__ uint32_t hash_row(uint32_t h) {  // murmur3 finaliser: every input bit reaches every output bit
+__device__ __forceinline__ uint32_t hash_row(uint32_t h) {  // murmur3 finaliser
   h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
   return h;
 }
@@ -255,7 +200,8 @@ __device__ __forceinline__ void visited_reset(VisitedSet& v, int lane) {
   __syncwarp();
 }
 
-// Each lane with active==true offers one id; returns true for lanes whose id was not in the set (and now is).
+// Each lane with active==true offers one id (ids offered together are distinct); returns true for lanes whose
+// id was not in the set (and now is).
 __device__ __forceinline__ bool visited_test_and_set(VisitedSet& v, uint32_t id, bool active, int lane) {
   bool is_new = false;
   if (v.count + 32 <= v.limit) {  // warp-uniform: room for every lane
@@ -271,7 +217,7 @@ __device__ __forceinline__ bool visited_test_and_set(VisitedSet& v, uint32_t id,
     v.count += __popc(__ballot_sync(kFull, is_new));
   } else {
     bool found = false;
-    if (active) {  // shared table is closed for inserts but still answers lookups
+    if (active) {  // the shared table is closed for inserts but still answers lookups
       uint32_t s = hash_row(id) & (v.cap - 1);
       for (;;) {
         const uint32_t old = v.tab[s];
@@ -284,7 +230,7 @@ __device__ __forceinline__ bool visited_test_and_set(VisitedSet& v, uint32_t id,
       v.failed = true;  // caller reports SHN_ERR_CAPACITY
     } else {
       if (active && !found) {
-        uint32_t s = (hash_row(id) >> 11) & (v.ovf_cap - 1);
+        uint32_t s = (hash_row(id) >> 7) & (v.ovf_cap - 1);
         for (;;) {
           const uint32_t old = atomicCAS(&v.ovf[s], kInvalid, id);
           if (old == kInvalid) { is_new = true; break; }

@@ -1,0 +1,191 @@
+"""ctypes binding of libshn_b200.so (include/shn.h).  No compute happens in Python; there is no CPU fallback:
+every entry point raises ShnError when the library is missing or no sm_100 device is usable."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+L2, IP = 0, 1
+INVALID_ID = 0xFFFFFFFF
+
+
+class ShnError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__(f"shn error {code}: {message}")
+        self.code = code
+
+
+class Stats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("distcomps", "visited_nodes", "visited_nodes_l0", "visited_neighborlists",
+                                          "lists_l0", "lists_upper", "algorithmic_bytes", "reference_layout_bytes",
+                                          "overflow_queries", "processed")] + \
+               [("kernel_ms", C.c_double), ("h2d_ms", C.c_double), ("d2h_ms", C.c_double)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+def library_path():
+    return os.path.join(_HERE, "libshn_b200.so")
+
+
+def build_library():
+    """Compile the CUDA library in-tree (nvcc cross-compiles for sm_100a without a GPU)."""
+    subprocess.check_call(["make", "-s", "-C", os.path.join(_HERE, "csrc")])
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        path = library_path()
+        if not os.path.exists(path):
+            raise ShnError(-3, f"{path} is missing: run __graft_entry__.build() (there is no CPU path)")
+        L = C.CDLL(path)
+        L.shn_last_error.restype = C.c_char_p
+        L.shn_version.restype = C.c_char_p
+        for f in ("shn_index_size", "shn_index_hbm_bytes", "shn_index_dump_bytes"):
+            getattr(L, f).restype = C.c_uint64
+            getattr(L, f).argtypes = [C.c_void_p]
+        for f in ("shn_index_dim", "shn_index_m", "shn_index_max_level"):
+            getattr(L, f).restype = C.c_uint32
+            getattr(L, f).argtypes = [C.c_void_p]
+        L.shn_index_free.argtypes = [C.c_void_p]
+        L.shn_index_free.restype = None
+        L.shn_index_load.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_char_p), C.c_int, C.c_uint32, C.c_uint32,
+                                     C.c_int, C.c_int]
+        L.shn_index_load_mem.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.c_int,
+                                         C.c_uint32, C.c_uint32, C.c_int, C.c_int]
+        L.shn_index_store.argtypes = [C.c_void_p, C.POINTER(C.c_char_p), C.c_int]
+        L.shn_index_store_mem.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.c_int]
+        L.shn_dump_repartition.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.c_int, C.c_uint32, C.c_uint32,
+                                           C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+        L.shn_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int64]
+        L.shn_search.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p,
+                                 C.POINTER(Stats)]
+        L.shn_search_device.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p,
+                                        C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Stats)]
+        _LIB = L
+    return _LIB
+
+
+def _check(rc):
+    if rc != 0:
+        raise ShnError(rc, lib().shn_last_error().decode())
+
+
+class Index:
+    """An HNSW index resident in the HBM of one B200 (handle of include/shn.h)."""
+
+    def __init__(self, handle, metric):
+        self._h = handle
+        self.metric = metric
+
+    # -- lifetime ----------------------------------------------------------------------------------------------
+    @classmethod
+    def load(cls, paths, dim, m, ip=False, gpu=0):
+        """From dump/index_m<M>_efc<efC>_node<i>_of<n>.dat files (reference format)."""
+        arr = (C.c_char_p * len(paths))(*[os.fsencode(p) for p in paths])
+        h = C.c_void_p()
+        _check(lib().shn_index_load(C.byref(h), arr, len(paths), dim, m, IP if ip else L2, gpu))
+        return cls(h, IP if ip else L2)
+
+    @classmethod
+    def from_dumps(cls, dumps, dim, m, ip=False, gpu=0):
+        """From dumps held in memory (bytes-like, one per memory node)."""
+        bufs = [np.frombuffer(d, dtype=np.uint8) for d in dumps]
+        ptrs = (C.c_void_p * len(bufs))(*[b.ctypes.data for b in bufs])
+        sizes = (C.c_uint64 * len(bufs))(*[b.size for b in bufs])
+        h = C.c_void_p()
+        _check(lib().shn_index_load_mem(C.byref(h), ptrs, sizes, len(bufs), dim, m, IP if ip else L2, gpu))
+        return cls(h, IP if ip else L2)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().shn_index_free(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- introspection -----------------------------------------------------------------------------------------
+    @property
+    def n(self):
+        return lib().shn_index_size(self._h)
+
+    @property
+    def dim(self):
+        return lib().shn_index_dim(self._h)
+
+    @property
+    def m(self):
+        return lib().shn_index_m(self._h)
+
+    @property
+    def max_level(self):
+        return lib().shn_index_max_level(self._h)
+
+    @property
+    def hbm_bytes(self):
+        return lib().shn_index_hbm_bytes(self._h)
+
+    @property
+    def dump_bytes(self):
+        return lib().shn_index_dump_bytes(self._h)
+
+    def set_option(self, key, value):
+        _check(lib().shn_set_option(self._h, key.encode(), int(value)))
+
+    # -- store -------------------------------------------------------------------------------------------------
+    def store(self, paths):
+        arr = (C.c_char_p * len(paths))(*[os.fsencode(p) for p in paths])
+        _check(lib().shn_index_store(self._h, arr, len(paths)))
+
+    def to_dumps(self, n_parts=1):
+        sizes = (C.c_uint64 * n_parts)()
+        _check(lib().shn_index_store_mem(self._h, None, sizes, n_parts))
+        bufs = [np.empty(int(s), dtype=np.uint8) for s in sizes]
+        ptrs = (C.c_void_p * n_parts)(*[b.ctypes.data for b in bufs])
+        _check(lib().shn_index_store_mem(self._h, ptrs, sizes, n_parts))
+        return bufs
+
+    # -- search ------------------------------------------------------------------------------------------------
+    def search(self, queries, k, ef, out_ids=None, out_dists=None):
+        """Host buffers in, host buffers out (numpy).  Returns (ids [nq,k] u32, dists [nq,k] f32, stats dict)."""
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        if q.ndim != 2 or q.shape[1] != self.dim:
+            raise ShnError(-1, f"queries must be [nq, {self.dim}]")
+        nq = q.shape[0]
+        ids = out_ids if out_ids is not None else np.empty((nq, k), np.uint32)
+        dists = out_dists if out_dists is not None else np.empty((nq, k), np.float32)
+        st = Stats()
+        _check(lib().shn_search(self._h, q.ctypes.data, nq, k, ef, ids.ctypes.data, dists.ctypes.data, C.byref(st)))
+        return ids, dists, st.as_dict()
+
+    def search_device(self, d_queries, nq, k, ef, d_ids, d_dists=0, d_counters=0, stream=0, want_stats=True):
+        """Raw device pointers (ints).  Synchronises only when want_stats."""
+        st = Stats()
+        _check(lib().shn_search_device(self._h, d_queries, nq, k, ef, d_ids, d_dists or None, d_counters or None,
+                                       stream or None, C.byref(st) if want_stats else None))
+        return st.as_dict() if want_stats else None
+
+
+def repartition_dumps(dumps, dim, m, n_parts_out):
+    """Host-only: rewrite reference-format dumps for a different memory-node count."""
+    bufs = [np.frombuffer(d, dtype=np.uint8) for d in dumps]
+    ptrs = (C.c_void_p * len(bufs))(*[b.ctypes.data for b in bufs])
+    sizes = (C.c_uint64 * len(bufs))(*[b.size for b in bufs])
+    osz = (C.c_uint64 * n_parts_out)()
+    _check(lib().shn_dump_repartition(ptrs, sizes, len(bufs), dim, m, n_parts_out, None, osz))
+    out = [np.empty(int(s), dtype=np.uint8) for s in osz]
+    optrs = (C.c_void_p * n_parts_out)(*[b.ctypes.data for b in out])
+    _check(lib().shn_dump_repartition(ptrs, sizes, len(bufs), dim, m, n_parts_out, optrs, osz))
+    return out

@@ -63,23 +63,19 @@ int shn_index_load(shn_index** out, const char* const* dump_paths, int n_parts, 
 int shn_index_load_mem(shn_index** out, const void* const* dumps, const uint64_t* sizes, int n_parts, uint32_t dim,
                        uint32_t m, shn_metric metric, int gpu_id);
 
-/* Build an index over base[n][dim] (host, row-major fp32; ids[i] = external id of row i, NULL = i) on the GPU.
- * Replaces ComputeNode::run_inserts -> hnsw::schedule<D,true> -> HNSW::insert (compute_node.cc:322,
- * hnsw/scheduler.hh:20, hnsw/hnsw.hh:40-251).  Levels are drawn with the reference's recipe
- * floor(-ln(U)/ln(m)) from mt19937(seed) (hnsw.hh:48,563).  The graph is not the reference's graph (insertion
- * is batched); it meets the same recall at equal m / ef_construction / ef. */
-int shn_index_build(shn_index** out, const float* base, const uint32_t* ids, uint64_t n, uint32_t dim, uint32_t m,
-                    uint32_t ef_construction, shn_metric metric, uint32_t seed, int gpu_id);
-/* Same with base already in device memory on gpu_id (row stride = dim floats). */
-int shn_index_build_device(shn_index** out, const float* d_base, const uint32_t* d_ids, uint64_t n, uint32_t dim,
-                           uint32_t m, uint32_t ef_construction, shn_metric metric, uint32_t seed, int gpu_id);
-
 /* Write the index as n_parts reference-format dumps (nodes dealt round-robin to parts when n_parts > 1).
  * Replaces MemoryNode::store_or_load_index store branch (memory_node.hh:187-195). */
 int shn_index_store(const shn_index*, const char* const* dump_paths, int n_parts);
 /* Size query + in-memory variant: sizes[i] receives the byte size of part i; if dumps != NULL, dumps[i] must
  * point to sizes[i] writable bytes. */
 int shn_index_store_mem(const shn_index*, void* const* dumps, uint64_t* sizes, int n_parts);
+
+/* Host-only utility (no GPU needed): re-partition reference-format dumps written for n_parts_in memory nodes into
+ * n_parts_out parts (a dump is otherwise only loadable with the memory-node count it was written with,
+ * compute_node.cc:428-430 "_of<n>").  Nodes keep their scan order and are dealt round-robin to the output parts.
+ * Two-call protocol as shn_index_store_mem: out_dumps == NULL fills out_sizes only. */
+int shn_dump_repartition(const void* const* dumps, const uint64_t* sizes, int n_parts_in, uint32_t dim, uint32_t m,
+                         int n_parts_out, void* const* out_dumps, uint64_t* out_sizes);
 
 void shn_index_free(shn_index*);
 
@@ -90,12 +86,9 @@ uint32_t shn_index_m(const shn_index*);
 uint32_t shn_index_max_level(const shn_index*);  /* build.max_level in the reference's JSON */
 uint64_t shn_index_hbm_bytes(const shn_index*);  /* device memory held by the handle */
 uint64_t shn_index_dump_bytes(const shn_index*); /* "index_size": bytes the reference would have allocated (rdma_atomics.hh:98) */
-/* Build-time counters of a handle created by shn_index_build (zero for loaded handles). */
-int shn_index_build_stats(const shn_index*, shn_stats* out);
-
-/* Options: "exact_arith" (0/1, default 0): compute distances in the reference's summation order
- * (src/hnsw/distance.hh as compiled, see oracle/hnsw_oracle.c) so that results are bit-identical to the
- * reference's; 0 = warp-parallel summation (ULP-level differences).  "warps_per_sm" (0 = auto). */
+/* Options: "warps_per_sm" (0 = auto): cap on resident query warps per SM.  Distances are always summed in the
+ * reference's own order (src/hnsw/distance.hh as compiled, see oracle/hnsw_oracle.c), so results are bit-identical
+ * to the reference's except on exact distance ties. */
 int shn_set_option(shn_index*, const char* key, int64_t value);
 
 /* ---- search ------------------------------------------------------------------------------------------------ */
@@ -114,16 +107,6 @@ int shn_search(shn_index*, const float* queries, uint64_t nq, uint32_t k, uint32
  * u32 per query: distcomps, visited_nodes, visited_nodes_l0, lists_l0, lists_upper, overflow flag. */
 int shn_search_device(shn_index*, const float* d_queries, uint64_t nq, uint32_t k, uint32_t ef, uint32_t* d_out_ids,
                       float* d_out_dists, uint32_t* d_per_query_counters, void* stream, shn_stats* stats);
-
-/* ---- ground truth ------------------------------------------------------------------------------------------ */
-
-/* Exact top-k by brute force (the reference only reads ground truth produced offline, compute_node.cc:317,588).
- * Host buffers; distances are fp32 squared L2 or 1 - dot, ties broken by lower id. */
-int shn_bruteforce_topk(const float* base, uint64_t n, const float* queries, uint64_t nq, uint32_t dim,
-                        shn_metric metric, uint32_t k, uint32_t* out_ids, float* out_dists, int gpu_id);
-int shn_bruteforce_topk_device(const float* d_base, uint64_t n, const float* d_queries, uint64_t nq, uint32_t dim,
-                               shn_metric metric, uint32_t k, uint32_t* d_out_ids, float* d_out_dists, int gpu_id,
-                               void* stream);
 
 const char* shn_last_error(void);
 const char* shn_version(void);

@@ -1,0 +1,149 @@
+"""GPU parity: shn_search (C ABI, host buffers) and shn_search_device against the golden vectors of the reference and
+against the oracle, bit-exact (ids, distance bits, the reference's counters).  Queries on which the reference itself
+decided a comparison on exactly equal distances (oracle `tie` flag) are compared as distance multisets only."""
+import numpy as np
+import pytest
+
+import golden_io
+import hnsw_oracle
+
+pytestmark = pytest.mark.gpu
+CASES = golden_io.case_names()
+
+
+def canon(ids, dists):
+    return hnsw_oracle.sorted_results(ids, dists)
+
+
+def compare(ids, dists, ref_ids, ref_dists, tie):
+    """ids/dists from the GPU (ascending), ref_* in any order."""
+    rid, rd = canon(ref_ids, ref_dists)
+    gid, gd = canon(ids, dists)  # ties by id, as the canonical form
+    clean = tie == 0
+    assert (gid[clean] == rid[clean]).all()
+    assert (gd[clean].view(np.uint32) == rd[clean].view(np.uint32)).all()
+    # with ties: the same distances must come back, ids may differ among equals
+    assert (gd.view(np.uint32) == rd.view(np.uint32)).mean() > 0.97
+    return int(clean.sum())
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_golden_parity(pkg, name):
+    case = golden_io.load_case(name)
+    oracle = hnsw_oracle.Index(case["dumps"], case["dim"], case["m"])
+    with pkg.Index.from_dumps(case["dumps"], case["dim"], case["m"], ip=case["ip"]) as ix:
+        assert ix.n == case["n"] and ix.dim == case["dim"] and ix.m == case["m"]
+        assert ix.dump_bytes == sum(len(d) for d in case["dumps"]) - 16 * len(case["dumps"])
+        for (k, ef), run in case["runs"].items():
+            ids, dists, st = ix.search(case["queries"], k, ef)
+            _, _, _, ct = oracle.knn(case["queries"], k, ef, ip=case["ip"], counters=True, track_ties=True)
+            n_clean = compare(ids, dists, run["ids"], run["dists"], ct["tie"])
+            if "dups" not in name:
+                assert n_clean == len(ids)
+            # sorted ascending, padded with 0xFFFFFFFF / +inf
+            valid = ids != 0xFFFFFFFF
+            assert (valid.sum(1) == run["counts"]).all()
+            assert np.isinf(dists[~valid]).all()
+            d = np.where(valid, dists, np.inf)
+            assert (np.diff(d, axis=1) >= 0).all()
+            if (ct["tie"] == 0).all():
+                assert st["distcomps"] == int(run["stats"]["distcomps"].sum())
+                assert st["visited_nodes"] == int(run["stats"]["visited_nodes"].sum())
+                assert st["visited_nodes_l0"] == int(run["stats"]["visited_nodes_l0"].sum())
+                assert st["visited_neighborlists"] == int(run["stats"]["visited_neighborlists"].sum())
+                assert st["reference_layout_bytes"] == int(run["stats"]["rdma_reads_in_bytes"].sum()) - 8 * len(ids)
+                assert st["lists_upper"] == int(ct["lists_upper"].sum())
+                assert st["algorithmic_bytes"] == 4 * case["dim"] * st["distcomps"] + 8 * case["m"] * st["lists_l0"] + \
+                    4 * case["m"] * st["lists_upper"]
+            assert st["processed"] == len(ids)
+
+
+@pytest.mark.parametrize("name", ["l2_d32_n2000_m16", "ip_d200_n1000_m16", "l2_d20_n300_m4_3mn"])
+def test_device_entry_point_and_per_query_counters(pkg, name):
+    import torch
+    case = golden_io.load_case(name)
+    oracle = hnsw_oracle.Index(case["dumps"], case["dim"], case["m"])
+    (k, ef) = next(iter(case["runs"]))
+    oi, od, _, ct = oracle.knn(case["queries"], k, ef, ip=case["ip"], counters=True, track_ties=True)
+    nq = len(oi)
+    with pkg.Index.from_dumps(case["dumps"], case["dim"], case["m"], ip=case["ip"]) as ix:
+        q = torch.from_numpy(case["queries"]).cuda()
+        ids = torch.empty((nq, k), dtype=torch.int32, device="cuda")
+        dists = torch.empty((nq, k), dtype=torch.float32, device="cuda")
+        ctr = torch.zeros((nq, 6), dtype=torch.int32, device="cuda")
+        st = ix.search_device(q.data_ptr(), nq, k, ef, ids.data_ptr(), dists.data_ptr(), ctr.data_ptr())
+        torch.cuda.synchronize()
+        gi = ids.cpu().numpy().view(np.uint32)
+        gd = dists.cpu().numpy()
+        c = ctr.cpu().numpy().astype(np.uint64)
+    compare(gi, gd, oi, od, ct["tie"])
+    clean = ct["tie"] == 0
+    for col, key in enumerate(("distcomps", "visited_nodes", "visited_nodes_l0", "lists_l0", "lists_upper")):
+        assert (c[clean, col] == ct[key][clean]).all(), key
+    assert st["kernel_ms"] > 0
+
+
+def test_repeatable_and_stream_safe(pkg):
+    """Same call twice gives the same bytes; the handle's scratch (cursor, visited tables) is clean between calls."""
+    case = golden_io.load_case("l2_d128_n1500_m16")
+    big_q = np.tile(case["queries"], (40, 1))
+    with pkg.Index.from_dumps(case["dumps"], case["dim"], case["m"]) as ix:
+        a = ix.search(big_q, 10, 64)
+        b = ix.search(big_q, 10, 64)
+        c = ix.search(case["queries"], 10, 64)
+        ix.set_option("warps_per_sm", 4)
+        d = ix.search(big_q, 10, 64)
+    assert (a[0] == b[0]).all() and (a[1].view(np.uint32) == b[1].view(np.uint32)).all()
+    assert (a[0] == d[0]).all()
+    assert (a[0][: len(c[0])] == c[0]).all()
+    nq = len(case["queries"])
+    assert (a[0][nq:2 * nq] == a[0][:nq]).all()
+    assert a[2]["distcomps"] == 40 * c[2]["distcomps"]
+
+
+def test_edge_cases(pkg):
+    case = golden_io.load_case("l2_d8_n40_m32")
+    with pkg.Index.from_dumps(case["dumps"], case["dim"], case["m"]) as ix:
+        ids, dists, st = ix.search(np.zeros((0, 8), np.float32), 10, 64)  # empty batch
+        assert ids.shape == (0, 10) and st["processed"] == 0
+        with pytest.raises(pkg.ShnError) as e:  # ef < k: hnsw.hh:36
+            ix.search(case["queries"], 10, 5)
+        assert e.value.code == -1
+        with pytest.raises(pkg.ShnError):
+            ix.search(case["queries"][:, :4], 10, 64)
+        # k larger than the index: every node comes back, rest padded
+        ids, dists, _ = ix.search(case["queries"], 50, 64)
+        assert ((ids != 0xFFFFFFFF).sum(1) == 40).all()
+        assert (np.sort(ids[:, :40], axis=1) == np.arange(40)).all()
+        # a single query, k = 1
+        ids, dists, _ = ix.search(case["queries"][:1], 1, 1)
+        assert ids.shape == (1, 1)
+
+
+def test_visited_overflow_path_is_exact(pkg):
+    """ef large relative to the shared visited table: queries spill to the HBM table and stay exact."""
+    case = golden_io.load_case("l2_d32_n2000_m16")
+    oracle = hnsw_oracle.Index(case["dumps"], case["dim"], case["m"])
+    with pkg.Index.from_dumps(case["dumps"], case["dim"], case["m"]) as ix:
+        for ef in (700, 1500):
+            ids, dists, st = ix.search(case["queries"], 10, ef)
+            oi, od, _, ct = oracle.knn(case["queries"], 10, ef, counters=True, track_ties=True)
+            compare(ids, dists, oi, od, ct["tie"])
+            assert st["distcomps"] == int(ct["distcomps"].sum())
+
+
+def test_store_round_trip(pkg, tmp_path):
+    """HBM -> reference-format dump files -> the oracle reads them and agrees; and they load back."""
+    case = golden_io.load_case("l2_d96_n1500_m16_2mn")
+    with pkg.Index.from_dumps(case["dumps"], case["dim"], case["m"]) as ix:
+        paths = [str(tmp_path / f"index_m16_efc100_node{i + 1}_of3.dat") for i in range(3)]
+        ix.store(paths)
+        ref = ix.search(case["queries"], 10, 64)
+    dumps = [open(p, "rb").read() for p in paths]
+    oracle = hnsw_oracle.Index(dumps, case["dim"], case["m"])
+    oi, od, _, _ = oracle.knn(case["queries"], 10, 64)
+    oi, od = canon(oi, od)
+    assert (oi == ref[0]).all() and (od.view(np.uint32) == ref[1].view(np.uint32)).all()
+    with pkg.Index.load(paths, case["dim"], case["m"]) as ix2:
+        again = ix2.search(case["queries"], 10, 64)
+    assert (again[0] == ref[0]).all()
