@@ -72,6 +72,7 @@ struct shn_index {
   DevBuf<float> q_stage, dist_stage;
   DevBuf<uint32_t> id_stage;
   int warps_per_sm = 0;
+  uint32_t vis_cap = 0;
 
   DeviceGraph view() const {
     DeviceGraph g;
@@ -226,7 +227,7 @@ void fill_stats(const shn_index* ix, const unsigned long long* t, uint64_t nq, s
 int run_search(shn_index* ix, const float* d_queries, uint64_t nq, uint32_t k, uint32_t ef, uint32_t* d_ids, float* d_dists,
                uint32_t* d_per_query, cudaStream_t stream, bool timed) {
   SearchConfig cfg;
-  cfg.k = k; cfg.ef = ef; cfg.ip = ix->metric == SHN_IP; cfg.warps_per_sm = ix->warps_per_sm; cfg.num_sms = ix->num_sms;
+  cfg.k = k; cfg.ef = ef; cfg.ip = ix->metric == SHN_IP; cfg.warps_per_sm = ix->warps_per_sm; cfg.num_sms = ix->num_sms; cfg.vis_cap = ix->vis_cap;
   int rc = prepare_workspace(ix, cfg, static_cast<uint32_t>(nq));
   if (rc != SHN_OK) return rc;
   if (timed) CU(cudaEventRecord(ix->ev[1], stream));
@@ -347,6 +348,11 @@ int shn_set_option(shn_index* ix, const char* key, int64_t value) {
   if (std::strcmp(key, "warps_per_sm") == 0) {
     if (value < 0 || value > 64) return fail(SHN_ERR_ARG, "warps_per_sm must be in [0, 64]");
     ix->warps_per_sm = static_cast<int>(value);
+    return SHN_OK;
+  }
+  if (std::strcmp(key, "visited_smem_entries") == 0) {
+    if (value < 0 || value > 32768) return fail(SHN_ERR_ARG, "visited_smem_entries must be in [0, 32768]");
+    ix->vis_cap = static_cast<uint32_t>(value);
     return SHN_OK;
   }
   return fail(SHN_ERR_ARG, "unknown option '%s'", key);

@@ -25,6 +25,7 @@ struct SearchConfig {
   uint32_t k, ef;
   bool ip;
   int warps_per_sm;  // 0 = auto
+  uint32_t vis_cap;  // entries of the shared-memory visited table per warp; 0 = auto
   int num_sms;
 };
 

@@ -36,7 +36,7 @@ __host__ __device__ inline size_t warp_smem_bytes(uint32_t q_floats, uint32_t ef
 }
 
 template <bool IP, int NCHUNK>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32) search_kernel(const SearchParams p) {
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 4) search_kernel(const SearchParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -154,14 +154,9 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) search_kernel(const Searc
       c_vl0 += cnt; c_dist += cnt;
       eval_rows<IP, NCHUNK>(g, s_q, s_rows, cnt, s_dist, lane);
 
-      // admission in list order against the running farthest distance (:456-465, heap.hh:34-41)
-      for (uint32_t i = 0; i < cnt; ++i) {
-        const float d = s_dist[i];
-        if (qsize < ef || d < qd[ef - 1]) {
-          const uint32_t at = queue_insert(qd, qi, qsize, ef, d, s_rows[i], lane);
-          if (at < lb) lb = at;
-        }
-      }
+      // admission against the running farthest distance (:456-465, heap.hh:34-41), all neighbours in one merge
+      const uint32_t at = queue_merge(qd, qi, qsize, ef, s_rows, s_dist, cnt, lane);
+      if (at < lb) lb = at;
     }
 
     // trim to k (:296-298); the reference reports ids in heap-array order, here ascending by distance
@@ -230,7 +225,7 @@ cudaError_t search_plan(const DeviceGraph& g, const SearchConfig& cfg, uint32_t 
                         uint32_t* vis_cap_out) {
   const uint32_t q_floats = g.row_f4 * 4;
   const uint32_t ef_cap = (cfg.ef + 31u) & ~31u;
-  uint32_t vis_cap = pick_vis_cap(cfg.ef, g.m0);
+  uint32_t vis_cap = cfg.vis_cap ? next_pow2(cfg.vis_cap) : pick_vis_cap(cfg.ef, g.m0);
   size_t bytes = kWarpsPerBlock * warp_smem_bytes(q_floats, ef_cap, vis_cap);
   while (bytes > 200 * 1024 && vis_cap > 1024) {
     vis_cap >>= 1;

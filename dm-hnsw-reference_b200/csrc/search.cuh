@@ -173,6 +173,79 @@ __device__ __forceinline__ uint32_t queue_insert(float* qd, uint32_t* qi, uint32
   return pos;
 }
 
+// Admit the candidates (s_rows[i], s_dist[i]), i < cnt <= 64, given in stored list order, in ONE merge.
+// Equivalent to the reference's one-by-one admission (hnsw.hh:456-465) whenever no two distances are equal: the
+// running farthest distance only shrinks, so what survives is exactly the ef smallest of old and new entries;
+// old entries stay ahead of new ones at equal distance and new ones keep their list order.  s_rows / s_dist are
+// used as scratch.  Returns the lowest queue position that received a new entry (kInvalid if none).
+__device__ __forceinline__ uint32_t queue_merge(float* qd, uint32_t* qi, uint32_t& qsize, uint32_t ef, uint32_t* s_rows,
+                                                float* s_dist, uint32_t cnt, int lane) {
+  const bool full = qsize == ef;
+  const float far = full ? qd[ef - 1] : __int_as_float(0x7f800000);
+  float d0 = 0.f, d1 = 0.f;
+  uint32_t r0 = 0, r1 = 0;
+  bool k0 = false, k1 = false;
+  if (static_cast<uint32_t>(lane) < cnt) { d0 = s_dist[lane]; r0 = s_rows[lane]; k0 = !full || d0 < far; }
+  if (static_cast<uint32_t>(lane) + 32 < cnt) { d1 = s_dist[lane + 32]; r1 = s_rows[lane + 32]; k1 = !full || d1 < far; }
+  const uint32_t m0 = __ballot_sync(kFull, k0), m1 = __ballot_sync(kFull, k1);
+  const uint32_t c0 = __popc(m0), c = c0 + __popc(m1);
+  if (c == 0) return kInvalid;
+  const uint32_t below = (1u << lane) - 1;
+  const uint32_t x0 = __popc(m0 & below), x1 = c0 + __popc(m1 & below);  // compacted index, list order
+  __syncwarp();
+  if (k0) s_dist[x0] = d0;
+  if (k1) s_dist[x1] = d1;
+  __syncwarp();
+  uint32_t rank0 = 0, rank1 = 0;
+  for (uint32_t y = 0; y < c; ++y) {
+    const float dy = s_dist[y];
+    rank0 += (dy < d0 || (dy == d0 && y < x0)) ? 1u : 0u;
+    rank1 += (dy < d1 || (dy == d1 && y < x1)) ? 1u : 0u;
+  }
+  __syncwarp();
+  if (k0) s_dist[rank0] = d0;  // survivors, ascending
+  if (k1) s_dist[rank1] = d1;
+  __syncwarp();
+  // position among the old entries: those with distance <= d stay ahead
+  uint32_t f0 = kInvalid, f1 = kInvalid;
+  if (k0) {
+    uint32_t lo = 0, hi = qsize;
+    while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (qd[mid] <= d0) lo = mid + 1; else hi = mid; }
+    f0 = lo + rank0;
+  }
+  if (k1) {
+    uint32_t lo = 0, hi = qsize;
+    while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (qd[mid] <= d1) lo = mid + 1; else hi = mid; }
+    f1 = lo + rank1;
+  }
+  uint32_t pmin = min(f0, f1);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) pmin = min(pmin, __shfl_xor_sync(kFull, pmin, o));
+  if (pmin >= ef) return kInvalid;
+  // old entries at or above pmin move up by the number of survivors strictly closer, highest block first
+  int hi = static_cast<int>(qsize);
+  while (hi > static_cast<int>(pmin)) {
+    const int lo = max(static_cast<int>(pmin), hi - 32);
+    const int j = lo + lane;
+    const bool act = j < hi;
+    float td = 0.f;
+    uint32_t ti = 0, shift = 0;
+    if (act) {
+      td = qd[j]; ti = qi[j];
+      for (uint32_t y = 0; y < c; ++y) shift += s_dist[y] < td ? 1u : 0u;
+    }
+    __syncwarp();
+    if (act && j + shift < ef) { qd[j + shift] = td; qi[j + shift] = ti; }
+    __syncwarp();
+    hi = lo;
+  }
+  if (k0 && f0 < ef) { qd[f0] = d0; qi[f0] = r0; }
+  if (k1 && f1 < ef) { qd[f1] = d1; qi[f1] = r1; }
+  __syncwarp();
+  qsize = min(ef, qsize + c);
+  return pmin;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // Exact visited set (the reference's unordered_set<RemotePtr>, hnsw.hh:408,441-443): open addressing in shared
 // memory; once `limit` keys are in, further keys spill to a per-warp table in HBM.  Never a false positive.

@@ -104,8 +104,8 @@ class Index:
         return cls(h, IP if ip else L2)
 
     def close(self):
-        if getattr(self, "_h", None):
-            lib().shn_index_free(self._h)
+        if getattr(self, "_h", None) and _LIB is not None:
+            _LIB.shn_index_free(self._h)
             self._h = None
 
     __del__ = close

@@ -20,9 +20,9 @@ ix = pkg.Index.from_dumps(dumps, dim, 16)
 q = torch.from_numpy(queries).cuda()
 ids = torch.empty((nq, 10), dtype=torch.int32, device="cuda")
 dists = torch.empty((nq, 10), dtype=torch.float32, device="cuda")
-for wps in (0, 8, 16, 24, 32):
-    ix.set_option("warps_per_sm", wps)
-    for ef in (16, 64, 256):
+for wps in (0, 1024, 2048, 4096):
+    ix.set_option("visited_smem_entries", wps)
+    for ef in (16, 64, 200, 256):
         ix.search_device(q.data_ptr(), nq, 10, ef, ids.data_ptr(), dists.data_ptr())
         best = 1e9
         for _ in range(3):
