@@ -1,0 +1,382 @@
+#!/usr/bin/env python
+"""bench.py — QPS of the batched HNSW search path at recall@10 >= 0.9 on a SIFT10M-shaped synthetic index.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+One step = one pass of the hot path (shn_search_device / shn_search) over one batch of synthetic queries.  The index
+is resident in HBM before the timed region; `value` is measured with the queries already in HBM (CUDA events on the
+launching stream), `e2e` goes through the host-buffer C-ABI call (H2D of the queries and D2H of the results inside the
+timed region).  With N > 1 every rank holds a replica of the index, takes its own shard of the queries (weak scaling)
+and the per-GPU top-k lists are gathered with an NCCL all-gather inside the timed region.
+
+--impl reference times the reference's own CPU search path (oracle/_ref/libshine_ref.so = /root/reference's hnsw.hh
+compiled unmodified; falls back to the plain-C port when that file is absent) on the host cores, on a bounded sample
+of the same workload.  The oracle is only ever executed in that arm and in the cpu_baseline leg.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")]
+import __graft_entry__ as ge  # noqa: E402
+
+WORKLOADS = {
+    # BASELINE.json configs[1]: SIFT10M-shaped synthetic, single B200, ef sweep 16-256
+    "sift10m": dict(n=10_000_000, dim=128, ip=False, m=16, efc=200, normalize=False,
+                    label="SIFT10M-shaped synthetic (10M x 128 fp32, L2, M=16, efC=200), ef sweep 16-256, k=10"),
+    # BASELINE.json configs[0]
+    "sift1m": dict(n=1_000_000, dim=128, ip=False, m=16, efc=200, normalize=False,
+                   label="SIFT1M-shaped synthetic (1M x 128 fp32, L2, M=16, efC=200), ef sweep 16-256, k=10"),
+    "tiny": dict(n=100_000, dim=128, ip=False, m=16, efc=200, normalize=False,
+                 label="100k x 128 fp32 synthetic (smoke-sized), L2, M=16, efC=200"),
+}
+EF_SWEEP = (16, 32, 64, 128, 256)
+K = 10
+RECALL_TARGET = 0.9
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def synth_rows(n, dim, seed, device, normalize=False, r=16, chunk=1 << 20):
+    """SURVEY 8d generator: x = A z / sqrt(r) + 0.05 eps with a fixed A (seed 1), z ~ N(0, I_r)."""
+    ga = torch.Generator(device="cpu").manual_seed(1)
+    a = torch.randn(dim, r, generator=ga).to(device)
+    g = torch.Generator(device=device).manual_seed(seed)
+    out = torch.empty((n, dim), dtype=torch.float32, device=device)
+    for s in range(0, n, chunk):
+        e = min(n, s + chunk)
+        z = torch.randn(e - s, r, generator=g, device=device)
+        x = z @ a.T / (r ** 0.5) + 0.05 * torch.randn(e - s, dim, generator=g, device=device)
+        if normalize:
+            x = x / x.norm(dim=1, keepdim=True)
+        out[s:e] = x
+    return out
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu):
+        self.gpu, self.proc, self.lines = gpu, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        self.thread.join(timeout=2)
+        sm, mx, reasons = [], 0, set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx = max(mx, float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, copy bandwidth)"
+    except (OSError, KeyError, ValueError):
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic_bytes():
+    """dram bytes per launch of the search kernel from the committed ncu summary, if there is one."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "search_kernel_traffic.json")) as f:
+            return json.load(f)
+    except (OSError, ValueError):
+        return None
+
+
+def build_index(pkg, wl, base_dev, gpu):
+    """Index over base_dev in HBM.  GPU construction when the library has it; otherwise the reference's own insert
+    path on the host cores (oracle/_ref) produces the dump that is then loaded — never inside a timed region."""
+    t0 = time.time()
+    if hasattr(pkg.Index, "build_device"):
+        ix = pkg.Index.build_device(base_dev.data_ptr(), wl["n"], wl["dim"], wl["m"], wl["efc"], ip=wl["ip"], seed=1234, gpu=gpu)
+        how = "gpu-built (shn_index_build_device)"
+    else:
+        import shine_ref
+        dumps, _, _ = shine_ref.build(base_dev.cpu().numpy(), m=wl["m"], efc=wl["efc"], ip=wl["ip"],
+                                      threads=os.cpu_count(), coroutines=4)
+        ix = pkg.Index.from_dumps(dumps, wl["dim"], wl["m"], ip=wl["ip"], gpu=gpu)
+        how = f"reference-built on {os.cpu_count()} host threads (oracle/_ref), loaded from its dump"
+    torch.cuda.synchronize()
+    return ix, how, time.time() - t0
+
+
+def ground_truth(base_dev, q_dev, k, ip):
+    """Exact top-k for the recall check (plumbing, not timed): fp32 blocked matmul + re-rank in fp64 on the top 4k."""
+    nq = q_dev.shape[0]
+    out = torch.empty((nq, k), dtype=torch.int64, device=q_dev.device)
+    step = 2_000_000
+    bn = None if ip else (base_dev * base_dev).sum(1)
+    for qs in range(0, nq, 1024):
+        q = q_dev[qs:qs + 1024]
+        best_d = best_i = None
+        for s in range(0, base_dev.shape[0], step):
+            b = base_dev[s:s + step]
+            d = -(q @ b.T) if ip else bn[s:s + step][None, :] - 2.0 * (q @ b.T)
+            dd, ii = torch.topk(d, min(4 * k, d.shape[1]), dim=1, largest=False)
+            ii += s
+            best_d = dd if best_d is None else torch.cat([best_d, dd], 1)
+            best_i = ii if best_i is None else torch.cat([best_i, ii], 1)
+            if best_d.shape[1] > 8 * k:
+                dd, sel = torch.topk(best_d, 4 * k, dim=1, largest=False)
+                best_d, best_i = dd, torch.gather(best_i, 1, sel)
+        cand = base_dev[best_i.reshape(-1)].reshape(q.shape[0], -1, base_dev.shape[1]).double()
+        qq = q.double()[:, None, :]
+        ex = -(cand * qq).sum(2) if ip else ((cand - qq) ** 2).sum(2)
+        _, sel = torch.topk(ex, k, dim=1, largest=False)
+        out[qs:qs + 1024] = torch.gather(best_i, 1, sel)
+    return out
+
+
+def recall_at_k(ids_dev, gt_dev):
+    k = gt_dev.shape[1]
+    hit = (ids_dev.long()[:, :, None] == gt_dev[:, None, :]).any(2).sum().item()
+    return hit / (gt_dev.shape[0] * k)
+
+
+def cpu_search(dumps, wl, queries_np, ef, threads, budget_s):
+    """The reference's CPU search path on a bounded sample: oracle/_ref when present (kind 'reference'), else the
+    plain-C port (kind 'port').  Returns (qps, kind, nq_done, seconds)."""
+    import shine_ref
+    if shine_ref.available():
+        probe = queries_np[:256]
+        _, _, _, _, s = shine_ref.search(dumps, wl["dim"], wl["m"], probe, K, ef, ip=wl["ip"], threads=threads, coroutines=4)
+        rate = len(probe) / max(s, 1e-6)
+        nq = int(min(len(queries_np), max(512, rate * budget_s)))
+        _, _, _, _, s = shine_ref.search(dumps, wl["dim"], wl["m"], queries_np[:nq], K, ef, ip=wl["ip"], threads=threads, coroutines=4)
+        return nq / s, "reference", nq, s
+    import hnsw_oracle
+    ix = hnsw_oracle.Index(dumps, wl["dim"], wl["m"])
+    probe = queries_np[:256]
+    t0 = time.time(); ix.knn(probe, K, ef, ip=wl["ip"], threads=threads); s = time.time() - t0
+    nq = int(min(len(queries_np), max(512, len(probe) / max(s, 1e-6) * budget_s)))
+    t0 = time.time(); ix.knn(queries_np[:nq], K, ef, ip=wl["ip"], threads=threads); s = time.time() - t0
+    return nq / s, "port", nq, s
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("SHN_BENCH_WORKLOAD", "sift10m"), choices=sorted(WORKLOADS))
+    ap.add_argument("--queries-per-step", type=int, default=1_000_000)
+    ap.add_argument("--recall-queries", type=int, default=10_000)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--ef", type=int, default=0, help="fix ef instead of picking the smallest with recall >= 0.9")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        log("bench: raising --warmup to 3 (timing rules)")
+        args.warmup = 3
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    wl = WORKLOADS[args.workload]
+
+    if args.impl == "reference" and rank != 0:
+        return  # rank 0 alone runs the CPU arm
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: there is no CPU path (the reference arm builds its index on the GPU too)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1 and args.impl == "b200":
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    pkg = ge.load_package()
+    nq = args.queries_per_step
+    base = synth_rows(wl["n"], wl["dim"], 1001, dev, wl["normalize"])
+    ix, how, build_s = build_index(pkg, wl, base, local_rank)
+    log(f"[rank {rank}] index: {how}, {build_s:.1f}s, n={ix.n} max_level={ix.max_level} hbm={ix.hbm_bytes / 1e9:.2f} GB")
+
+    # query batches: held-out draws of the same model; each rank its own shard (seed), 4 distinct batches rotate
+    n_batches = 4
+    batches = [synth_rows(nq, wl["dim"], 2002 + 1000 * rank + b, dev, wl["normalize"]) for b in range(n_batches)]
+    ids = torch.empty((nq, K), dtype=torch.int32, device=dev)
+    dists = torch.empty((nq, K), dtype=torch.float32, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    # ---- ef selection: the smallest ef of the sweep with recall@10 >= 0.9 (rank 0 decides) -----------------------
+    nrec = min(args.recall_queries, nq)
+    gt = ground_truth(base, batches[0][:nrec], K, wl["ip"])
+    sweep = []
+    for ef in EF_SWEEP:
+        st = ix.search_device(batches[0].data_ptr(), nq, K, ef, ids.data_ptr(), dists.data_ptr(), stream=stream)
+        rec = recall_at_k(ids[:nrec], gt)
+        sweep.append(dict(ef=ef, recall=round(rec, 4), qps=round(nq / st["kernel_ms"] * 1e3, 1),
+                          distcomps_per_query=round(st["distcomps"] / nq, 1),
+                          alg_bytes_per_query=round(st["algorithmic_bytes"] / nq, 1)))
+        log(f"[rank {rank}] sweep {sweep[-1]}")
+    ef = args.ef or next((s["ef"] for s in sweep if s["recall"] >= RECALL_TARGET), EF_SWEEP[-1])
+    recall = next((s["recall"] for s in sweep if s["ef"] == ef), None)
+
+    peak, peak_src = measured_peak()
+
+    if args.impl == "reference":
+        threads = os.cpu_count()
+        dumps = [d.tobytes() for d in ix.to_dumps(1)]
+        qnp = batches[0].cpu().numpy()
+        per_step = []
+        sample = None
+        for i in range(args.warmup + args.steps):
+            qps, kind, done, secs = cpu_search(dumps, wl, qnp, ef, threads, max(2.0, args.cpu_seconds / max(1, args.steps)))
+            sample = f"{done} queries of the step's batch per step (ef={ef}, k={K}), {secs:.1f}s"
+            if i >= args.warmup:
+                per_step.append((done, secs))
+        tot_q = sum(d for d, _ in per_step); tot_s = sum(s for _, s in per_step)
+        val = tot_q / tot_s
+        line = dict(metric="queries_per_sec at recall@10>=0.9", value=round(val, 1), unit="queries/s", impl="reference",
+                    n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=round(1e3 * tot_s / len(per_step), 3),
+                    higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                    config=dict(workload=wl["label"], ef=ef, k=K, recall_at_10=recall, index=how),
+                    cpu_baseline=dict(value=round(val, 1), unit="queries/s", cores=threads, kind=kind, sample=sample),
+                    e2e=dict(value=round(val, 1), unit="queries/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+        print(json.dumps(line), flush=True)
+        return
+
+    # ---- device-resident timing (value) ------------------------------------------------------------------------
+    def step_device(i):
+        return ix.search_device(batches[i % n_batches].data_ptr(), nq, K, ef, ids.data_ptr(), dists.data_ptr(),
+                                stream=stream, want_stats=False)
+
+    gathered = [torch.empty_like(ids) for _ in range(world)] if dist else None
+
+    def barrier():
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step_device(i)
+        if dist:
+            dist.all_gather(gathered, ids)
+    barrier()
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kern_ms = []
+    ev0.record()
+    for i in range(args.steps):
+        step_device(args.warmup + i)
+        if dist:
+            dist.all_gather(gathered, ids)  # per-GPU top-k lists -> every rank
+    ev1.record()
+    barrier()
+    total_ms = ev0.elapsed_time(ev1)
+    clk = clocks.stop()
+
+    # kernel-only duration + algorithmic bytes of the dominant kernel, measured live (events inside the C ABI on the
+    # launching stream), same batches
+    alg_bytes = 0
+    for i in range(args.steps):
+        st = ix.search_device(batches[(args.warmup + i) % n_batches].data_ptr(), nq, K, ef, ids.data_ptr(), dists.data_ptr(),
+                              stream=stream)
+        kern_ms.append(st["kernel_ms"]); alg_bytes += st["algorithmic_bytes"]
+    kern_avg_ms = float(np.mean(kern_ms))
+    achieved = alg_bytes / args.steps / (kern_avg_ms * 1e-3) / 1e9
+
+    # ---- end to end through the host-buffer C-ABI call (e2e) -------------------------------------------------------
+    host_q = [torch.empty((nq, wl["dim"]), dtype=torch.float32).pin_memory() for _ in range(2)]
+    for h, b in zip(host_q, batches):
+        h.copy_(b)
+    host_ids = torch.empty((nq, K), dtype=torch.int32).pin_memory()
+    host_d = torch.empty((nq, K), dtype=torch.float32).pin_memory()
+
+    def step_host(i):
+        ix.search(host_q[i % 2].numpy(), K, ef, out_ids=host_ids.numpy().view(np.uint32), out_dists=host_d.numpy())
+
+    for i in range(2):
+        step_host(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step_host(i)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+
+    # max over ranks
+    if dist:
+        t = torch.tensor([total_ms, e2e_s * 1e3], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, e2e_ms = t.tolist()
+        e2e_s = e2e_ms / 1e3
+    value = world * nq * args.steps / (total_ms * 1e-3)
+    e2e = world * nq * args.steps / e2e_s
+
+    if rank != 0:
+        if dist:
+            dist.destroy_process_group()
+        return
+
+    traffic = ncu_traffic_bytes()
+    line = dict(metric="queries_per_sec at recall@10>=0.9", value=round(value, 1), unit="queries/s", n_gpus=world,
+                steps=args.steps, warmup=args.warmup, ms_per_step=round(total_ms / args.steps, 3), higher_is_better=True,
+                scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                config=dict(workload=wl["label"], ef=ef, k=K, recall_at_10=recall, queries_per_step_per_gpu=nq,
+                            index=how, index_build_s=round(build_s, 1), l2_policy="index (>= 6 GB at 10M rows) and the "
+                            "rotating query batches are larger than the 126 MB L2; no flush",
+                            parallelism=f"replica x{world}, queries sharded, NCCL all-gather of top-k" if world > 1 else "single GPU"),
+                roofline=dict(bound="hbm", achieved=round(achieved, 1), peak=peak, unit="GB/s", frac=round(achieved / peak, 4),
+                              traffic=(traffic or {}).get("dram_bytes_per_launch"), peak_source=peak_src,
+                              kernel="search_kernel", kernel_ms=round(kern_avg_ms, 3),
+                              algorithmic_bytes_per_launch=alg_bytes // args.steps),
+                e2e=dict(value=round(e2e, 1), unit="queries/s", h2d_bytes_per_step=nq * wl["dim"] * 4,
+                         d2h_bytes_per_step=nq * K * 8),
+                gpu_launches=args.steps, clocks=clk, sweep=sweep)
+
+    if world == 1:
+        dumps = [d.tobytes() for d in ix.to_dumps(1)]
+        qps, kind, done, secs = cpu_search(dumps, wl, batches[0].cpu().numpy(), ef, os.cpu_count(), args.cpu_seconds)
+        line["cpu_baseline"] = dict(value=round(qps, 1), unit="queries/s", cores=os.cpu_count(), kind=kind,
+                                    sample=f"first {done} queries of batch 0 (ef={ef}, k={K}), {secs:.1f}s, {os.cpu_count()} threads x 4 coroutines")
+    print(json.dumps(line), flush=True)
+    if dist:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

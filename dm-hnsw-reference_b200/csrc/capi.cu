@@ -73,6 +73,9 @@ struct shn_index {
   DevBuf<uint32_t> id_stage;
   int warps_per_sm = 0;
   uint32_t vis_cap = 0;
+  shn_stats build_stats{};
+  uint32_t batch_max = 0;
+  bool built = false;
 
   DeviceGraph view() const {
     DeviceGraph g;
@@ -281,6 +284,105 @@ int shn_index_load(shn_index** out, const char* const* dump_paths, int n_parts, 
   return shn_index_load_mem(out, ptrs.data(), sizes.data(), n_parts, dim, m, metric, gpu_id);
 }
 
+int shn_index_build_device(shn_index** out, const float* d_base, const uint32_t* d_ids, uint64_t n, uint32_t dim,
+                           uint32_t m, uint32_t ef_construction, shn_metric metric, uint32_t seed, int gpu_id) {
+  if (!out || !d_base) return fail(SHN_ERR_ARG, "null argument");
+  if (n == 0 || n >= (1ull << 30)) return fail(SHN_ERR_ARG, "n must be in [1, 2^30)");
+  if (dim == 0 || m < 2 || m > 32) return fail(SHN_ERR_ARG, "need dim >= 1 and 2 <= m <= 32");
+  if (ef_construction == 0 || ef_construction > 4096) return fail(SHN_ERR_ARG, "ef_construction must be in [1, 4096]");
+  shn_index* ix = nullptr;
+  int rc = new_handle(&ix, gpu_id, metric);
+  if (rc != SHN_OK) return rc;
+  auto bail = [&](int code) { shn_index_free(ix); return code; };
+#define CUB(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return bail(fail(SHN_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e__))); } while (0)
+  std::vector<uint32_t> level;
+  draw_levels(n, m, seed, level);
+  std::vector<uint32_t> up_base(n, kInvalid);
+  uint64_t n_up = 0;
+  uint32_t max_level = 0;
+  for (uint64_t i = 0; i < n; ++i) {
+    if (level[i]) { up_base[i] = static_cast<uint32_t>(n_up); n_up += level[i]; }
+    max_level = std::max(max_level, level[i]);
+  }
+  ix->n = static_cast<uint32_t>(n); ix->dim = dim; ix->m = m; ix->n_up = n_up; ix->max_level = max_level;
+  ix->row_f4 = ((dim + 3) / 4 + 1) & ~1u;
+  const size_t row_floats = static_cast<size_t>(ix->row_f4) * 4, m0 = 2ull * m;
+  CUB(cudaMalloc(&ix->d_vec, n * row_floats * sizeof(float)));
+  CUB(cudaMalloc(&ix->d_l0, n * m0 * sizeof(uint32_t)));
+  CUB(cudaMalloc(&ix->d_up_base, n * sizeof(uint32_t)));
+  CUB(cudaMalloc(&ix->d_up, std::max<size_t>(n_up, 1) * m * sizeof(uint32_t)));
+  CUB(cudaMalloc(&ix->d_ext_id, n * sizeof(uint32_t)));
+  CUB(cudaMalloc(&ix->d_level, n * sizeof(uint32_t)));
+  ix->hbm_bytes = n * (row_floats * 4 + m0 * 4 + 12) + std::max<size_t>(n_up, 1) * m * 4;
+  cudaStream_t s = ix->stream;
+  CUB(cudaEventRecord(ix->ev[0], s));
+  if (row_floats != dim) CUB(cudaMemsetAsync(ix->d_vec, 0, n * row_floats * sizeof(float), s));
+  CUB(cudaMemcpy2DAsync(ix->d_vec, row_floats * sizeof(float), d_base, dim * sizeof(float), dim * sizeof(float), n,
+                        cudaMemcpyDeviceToDevice, s));
+  CUB(cudaMemsetAsync(ix->d_l0, 0xFF, n * m0 * sizeof(uint32_t), s));
+  CUB(cudaMemsetAsync(ix->d_up, 0xFF, std::max<size_t>(n_up, 1) * m * sizeof(uint32_t), s));
+  CUB(cudaMemcpyAsync(ix->d_up_base, up_base.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+  CUB(cudaMemcpyAsync(ix->d_level, level.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+  if (d_ids) {
+    CUB(cudaMemcpyAsync(ix->d_ext_id, d_ids, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+  } else {
+    std::vector<uint32_t> ids(n);
+    for (uint64_t i = 0; i < n; ++i) ids[i] = static_cast<uint32_t>(i);
+    CUB(cudaMemcpyAsync(ix->d_ext_id, ids.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    CUB(cudaStreamSynchronize(s));
+  }
+  BuildJob job;
+  job.g = ix->view();
+  job.l0_w = ix->d_l0; job.up_w = ix->d_up; job.level_dev = ix->d_level; job.level_host = &level;
+  job.n = ix->n; job.efc = ef_construction; job.batch_max = ix->batch_max; job.ip = metric == SHN_IP; job.num_sms = ix->num_sms;
+  cudaError_t e = build_graph(job, s);
+  if (e != cudaSuccess) return bail(fail(SHN_ERR_CUDA, "build_graph: %s", cudaGetErrorString(e)));
+  if (job.failed) return bail(fail(SHN_ERR_CAPACITY, "%llu inserts overflowed the visited set", job.failed));
+  CUB(cudaEventRecord(ix->ev[1], s));
+  CUB(cudaStreamSynchronize(s));
+  float ms = 0.f;
+  CUB(cudaEventElapsedTime(&ms, ix->ev[0], ix->ev[1]));
+  ix->ep_row = job.ep_row; ix->max_level_of_ep = job.ep_level;
+  uint64_t db = 0;
+  for (uint64_t r = 0; r < n; ++r) db += ref_alloc_bytes(dim, m, level[r]);
+  ix->dump_bytes = db;
+  ix->built = true;
+  ix->build_stats.distcomps = job.distcomps;
+  ix->build_stats.processed = n;
+  ix->build_stats.kernel_ms = ms;
+  *out = ix;
+  return SHN_OK;
+#undef CUB
+}
+
+int shn_index_build(shn_index** out, const float* base, const uint32_t* ids, uint64_t n, uint32_t dim, uint32_t m,
+                    uint32_t ef_construction, shn_metric metric, uint32_t seed, int gpu_id) {
+  if (!out || !base) return fail(SHN_ERR_ARG, "null argument");
+  if (n == 0 || dim == 0) return fail(SHN_ERR_ARG, "empty base");
+  int sms = 0;
+  int rc = select_device(gpu_id, &sms);
+  if (rc != SHN_OK) return rc;
+  float* d_base = nullptr;
+  uint32_t* d_ids = nullptr;
+  CU(cudaMalloc(&d_base, n * dim * sizeof(float)));
+  cudaError_t e = cudaMemcpy(d_base, base, n * dim * sizeof(float), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && ids) {
+    e = cudaMalloc(&d_ids, n * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMemcpy(d_ids, ids, n * sizeof(uint32_t), cudaMemcpyHostToDevice);
+  }
+  if (e != cudaSuccess) { cudaFree(d_base); cudaFree(d_ids); return fail(SHN_ERR_CUDA, "staging the base: %s", cudaGetErrorString(e)); }
+  rc = shn_index_build_device(out, d_base, d_ids, n, dim, m, ef_construction, metric, seed, gpu_id);
+  cudaFree(d_base); cudaFree(d_ids);
+  return rc;
+}
+
+int shn_index_build_stats(const shn_index* ix, shn_stats* out) {
+  if (!ix || !out) return fail(SHN_ERR_ARG, "null argument");
+  if (!ix->built) return fail(SHN_ERR_STATE, "the index was loaded, not built");
+  *out = ix->build_stats;
+  return SHN_OK;
+}
+
 int shn_index_store_mem(const shn_index* ix, void* const* dumps, uint64_t* sizes, int n_parts) {
   if (!ix || !sizes || n_parts < 1 || n_parts > 65535) return fail(SHN_ERR_ARG, "bad arguments");
   HostGraph g;
@@ -348,6 +450,11 @@ int shn_set_option(shn_index* ix, const char* key, int64_t value) {
   if (std::strcmp(key, "warps_per_sm") == 0) {
     if (value < 0 || value > 64) return fail(SHN_ERR_ARG, "warps_per_sm must be in [0, 64]");
     ix->warps_per_sm = static_cast<int>(value);
+    return SHN_OK;
+  }
+  if (std::strcmp(key, "build_batch_max") == 0) {
+    if (value < 0 || value > (1 << 20)) return fail(SHN_ERR_ARG, "build_batch_max must be in [0, 2^20]");
+    ix->batch_max = static_cast<uint32_t>(value);
     return SHN_OK;
   }
   if (std::strcmp(key, "visited_smem_entries") == 0) {

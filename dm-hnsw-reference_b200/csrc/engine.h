@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <vector>
 
 #include "graph.h"
 
@@ -42,5 +43,24 @@ cudaError_t search_launch(const DeviceGraph& g, const SearchConfig& cfg, const f
 // Exact top-k by brute force over base[n][dim] (row stride = dim floats): ids are row numbers.
 cudaError_t bruteforce_launch(const float* d_base, uint64_t n, const float* d_queries, uint32_t nq, uint32_t dim, bool ip,
                               uint32_t k, uint32_t* d_ids, float* d_dists, cudaStream_t stream);
+
+// ---- construction (build.cu) ------------------------------------------------------------------------------------
+struct BuildJob {
+  DeviceGraph g;             // vec / l0 / up_base / up / ext_id / n / dim / m / m0 / row_f4 (entry point is filled per batch)
+  uint32_t* l0_w = nullptr;  // writable aliases of g.l0 / g.up, all kInvalid on entry
+  uint32_t* up_w = nullptr;
+  const uint32_t* level_dev = nullptr;
+  const std::vector<uint32_t>* level_host = nullptr;
+  uint32_t n = 0, efc = 0, batch_max = 0;
+  bool ip = false;
+  int num_sms = 0;
+  void (*progress)(uint64_t done, uint64_t total) = nullptr;
+  // results
+  uint32_t ep_row = 0, ep_level = 0;
+  unsigned long long distcomps = 0, failed = 0;
+};
+
+void draw_levels(uint64_t n, uint32_t m, uint32_t seed, std::vector<uint32_t>& level);
+cudaError_t build_graph(BuildJob& job, cudaStream_t stream);
 
 }  // namespace shn

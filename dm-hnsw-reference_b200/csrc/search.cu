@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 4) search_kernel(const Se
   vis.count = 0; vis.ovf_count = 0; vis.failed = false;
 
   unsigned long long t_dist = 0, t_vup = 0, t_vl0 = 0, t_l0 = 0, t_lup = 0, t_ovf = 0, t_fail = 0;
-  const uint32_t m = g.m, m0 = g.m0, ef = p.ef;
+  const uint32_t ef = p.ef;
 
   for (;;) {
     uint32_t q = 0;
@@ -83,81 +83,17 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 4) search_kernel(const Se
 
     // search_for_one<without_lock>: levels ep.level .. 1 (hnsw.hh:341-391)
     for (uint32_t level = g.ep_level; level > 0; --level) {
-      bool changed = true;
-      while (changed) {
-        changed = false;
-        const uint32_t* list = g.up + (static_cast<size_t>(__ldg(g.up_base + cur)) + (level - 1)) * m;
-        ++c_lup;
-        const uint32_t nb = lane < m ? __ldg(list + lane) : kInvalid;
-        const uint32_t valid = __ballot_sync(kFull, nb != kInvalid);  // lists are stored compacted
-        const uint32_t cnt = __popc(valid);
-        if (nb != kInvalid) s_rows[lane] = nb;
-        __syncwarp();
-        if (cnt == 0) break;
-        eval_rows<IP, NCHUNK>(g, s_q, s_rows, cnt, s_dist, lane);
-        c_vup += cnt; c_dist += cnt;
-        // sequential scan with strict '<' (hnsw.hh:378-382) == first index of the list minimum, if it beats closest
-        float bd = lane < cnt ? s_dist[lane] : __int_as_float(0x7f800000);
-        uint32_t bi = lane;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          const float od = __shfl_xor_sync(kFull, bd, o);
-          const uint32_t oi = __shfl_xor_sync(kFull, bi, o);
-          if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
-        }
-        if (bi < cnt && bd < closest) {
-          closest = bd;
-          cur = s_rows[bi];
-          changed = true;
-        }
-        __syncwarp();
-      }
+      while (greedy_step<IP, NCHUNK>(g, s_q, level, cur, closest, s_rows, s_dist, c_dist, c_vup, c_lup, lane)) {}
     }
 
     // hnsw.hh:285-288 — distance recomputed (same bits), seed of the level-0 search
     ++c_dist;
-    uint32_t qsize = 0;
     if (lane == 0) { qd[0] = closest; qi[0] = cur; }
-    qsize = 1;
+    uint32_t qsize = 1;
     visited_test_and_set(vis, cur, lane == 0, lane);
-    uint32_t lb = 0;  // every entry below lb is expanded
 
-    // search_level<without_lock>(ef, level 0) (hnsw.hh:417-473)
-    for (;;) {
-      // next_candidates.pop(): the closest entry not yet expanded
-      uint32_t pos = kInvalid;
-      for (uint32_t b = lb & ~31u; b < qsize; b += 32) {
-        const uint32_t j = b + lane;
-        const bool un = j < qsize && j >= lb && !(qi[j] & kExpanded);
-        const uint32_t mask = __ballot_sync(kFull, un);
-        if (mask) { pos = b + __ffs(mask) - 1; break; }
-      }
-      if (pos == kInvalid) break;  // what is left of next_candidates is farther than top_candidates.top() (:424)
-      const uint32_t cand = qi[pos];
-      __syncwarp();
-      if (lane == 0) qi[pos] = cand | kExpanded;
-      lb = pos + 1;
-      ++c_l0;
-
-      // read_neighborlist + the visited filter, in stored order (:437-443)
-      uint32_t cnt = 0;
-      for (uint32_t j0 = 0; j0 < m0; j0 += 32) {
-        const uint32_t j = j0 + lane;
-        const uint32_t nb = j < m0 ? __ldg(g.l0 + static_cast<size_t>(cand) * m0 + j) : kInvalid;
-        const bool fresh = visited_test_and_set(vis, nb, nb != kInvalid, lane);
-        const uint32_t mask = __ballot_sync(kFull, fresh);
-        if (fresh) s_rows[cnt + __popc(mask & ((1u << lane) - 1))] = nb;
-        cnt += __popc(mask);
-      }
-      __syncwarp();
-      if (cnt == 0) continue;
-      c_vl0 += cnt; c_dist += cnt;
-      eval_rows<IP, NCHUNK>(g, s_q, s_rows, cnt, s_dist, lane);
-
-      // admission against the running farthest distance (:456-465, heap.hh:34-41), all neighbours in one merge
-      const uint32_t at = queue_merge(qd, qi, qsize, ef, s_rows, s_dist, cnt, lane);
-      if (at < lb) lb = at;
-    }
+    // search_level<without_lock>(ef, level 0) (hnsw.hh:407-476)
+    beam_search<IP, NCHUNK>(g, s_q, 0, ef, qd, qi, qsize, s_rows, s_dist, vis, c_dist, c_vl0, c_l0, lane);
 
     // trim to k (:296-298); the reference reports ids in heap-array order, here ascending by distance
     for (uint32_t j = lane; j < p.k; j += 32) {

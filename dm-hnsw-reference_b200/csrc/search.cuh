@@ -318,4 +318,88 @@ __device__ __forceinline__ bool visited_test_and_set(VisitedSet& v, uint32_t id,
   return is_new;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// ef-bounded best-first search on one level (HNSW::search_level, hnsw.hh:407-476).  On entry the queue holds the
+// seed entries (unexpanded) and the visited set holds their rows.  Level 0 reads the 2m-wide lists, upper levels the
+// m-wide ones.  Counters: distance computations / nodes visited / lists read on this level.
+// ---------------------------------------------------------------------------------------------------------------
+template <bool IP, int NCHUNK>
+__device__ __forceinline__ void beam_search(const DeviceGraph& g, const float* s_q, uint32_t level, uint32_t ef, float* qd,
+                                            uint32_t* qi, uint32_t& qsize, uint32_t* s_rows, float* s_dist, VisitedSet& vis,
+                                            uint32_t& c_dist, uint32_t& c_vis, uint32_t& c_lists, int lane) {
+  const uint32_t width = level == 0 ? g.m0 : g.m;
+  uint32_t lb = 0;  // every entry below lb is expanded
+  for (;;) {
+    // next_candidates.pop(): the closest entry not yet expanded
+    uint32_t pos = kInvalid;
+    for (uint32_t b = lb & ~31u; b < qsize; b += 32) {
+      const uint32_t j = b + lane;
+      const bool un = j < qsize && j >= lb && !(qi[j] & kExpanded);
+      const uint32_t mask = __ballot_sync(kFull, un);
+      if (mask) { pos = b + __ffs(mask) - 1; break; }
+    }
+    if (pos == kInvalid) break;  // what is left of next_candidates is farther than top_candidates.top() (:424)
+    const uint32_t cand = qi[pos];
+    __syncwarp();
+    if (lane == 0) qi[pos] = cand | kExpanded;
+    lb = pos + 1;
+    ++c_lists;
+
+    // read_neighborlist + the visited filter, in stored order (:437-443)
+    const uint32_t* list = level == 0 ? g.l0 + static_cast<size_t>(cand) * g.m0
+                                      : g.up + (static_cast<size_t>(__ldg(g.up_base + cand)) + (level - 1)) * g.m;
+    uint32_t cnt = 0;
+    for (uint32_t j0 = 0; j0 < width; j0 += 32) {
+      const uint32_t j = j0 + lane;
+      const uint32_t nb = j < width ? __ldg(list + j) : kInvalid;
+      const bool fresh = visited_test_and_set(vis, nb, nb != kInvalid, lane);
+      const uint32_t mask = __ballot_sync(kFull, fresh);
+      if (fresh) s_rows[cnt + __popc(mask & ((1u << lane) - 1))] = nb;
+      cnt += __popc(mask);
+    }
+    __syncwarp();
+    if (cnt == 0) continue;
+    c_vis += cnt; c_dist += cnt;
+    eval_rows<IP, NCHUNK>(g, s_q, s_rows, cnt, s_dist, lane);
+
+    // admission against the running farthest distance (:456-465, heap.hh:34-41), all neighbours in one merge
+    const uint32_t at = queue_merge(qd, qi, qsize, ef, s_rows, s_dist, cnt, lane);
+    if (at < lb) lb = at;
+  }
+}
+
+// One step of search_for_one (hnsw.hh:342-391) on `level`: scan the whole list of `cur`, move to the list minimum if
+// it is strictly closer.  Returns true if cur changed.
+template <bool IP, int NCHUNK>
+__device__ __forceinline__ bool greedy_step(const DeviceGraph& g, const float* s_q, uint32_t level, uint32_t& cur,
+                                            float& closest, uint32_t* s_rows, float* s_dist, uint32_t& c_dist,
+                                            uint32_t& c_vis, uint32_t& c_lists, int lane) {
+  const uint32_t* list = g.up + (static_cast<size_t>(__ldg(g.up_base + cur)) + (level - 1)) * g.m;
+  ++c_lists;
+  const uint32_t nb = static_cast<uint32_t>(lane) < g.m ? __ldg(list + lane) : kInvalid;
+  const uint32_t cnt = __popc(__ballot_sync(kFull, nb != kInvalid));  // lists are stored compacted
+  if (nb != kInvalid) s_rows[lane] = nb;
+  __syncwarp();
+  if (cnt == 0) return false;
+  eval_rows<IP, NCHUNK>(g, s_q, s_rows, cnt, s_dist, lane);
+  c_vis += cnt; c_dist += cnt;
+  // sequential scan with strict '<' (hnsw.hh:378-382) == first index of the list minimum, if it beats closest
+  float bd = static_cast<uint32_t>(lane) < cnt ? s_dist[lane] : __int_as_float(0x7f800000);
+  uint32_t bi = lane;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float od = __shfl_xor_sync(kFull, bd, o);
+    const uint32_t oi = __shfl_xor_sync(kFull, bi, o);
+    if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
+  }
+  bool changed = false;
+  if (bi < cnt && bd < closest) {
+    closest = bd;
+    cur = s_rows[bi];
+    changed = true;
+  }
+  __syncwarp();
+  return changed;
+}
+
 }  // namespace shn

@@ -63,6 +63,10 @@ def lib():
         L.shn_index_store_mem.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.c_int]
         L.shn_dump_repartition.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.c_int, C.c_uint32, C.c_uint32,
                                            C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+        L.shn_index_build.argtypes = [C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32,
+                                      C.c_uint32, C.c_int, C.c_uint32, C.c_int]
+        L.shn_index_build_device.argtypes = L.shn_index_build.argtypes
+        L.shn_index_build_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
         L.shn_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int64]
         L.shn_search.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p,
                                  C.POINTER(Stats)]
@@ -102,6 +106,28 @@ class Index:
         h = C.c_void_p()
         _check(lib().shn_index_load_mem(C.byref(h), ptrs, sizes, len(bufs), dim, m, IP if ip else L2, gpu))
         return cls(h, IP if ip else L2)
+
+    @classmethod
+    def build(cls, base, m, efc, ip=False, seed=1234, ids=None, gpu=0):
+        """GPU construction over host rows base[n][dim] (shn_index_build)."""
+        b = np.ascontiguousarray(base, dtype=np.float32)
+        i = np.ascontiguousarray(ids, dtype=np.uint32) if ids is not None else None
+        h = C.c_void_p()
+        _check(lib().shn_index_build(C.byref(h), b.ctypes.data, i.ctypes.data if i is not None else None, b.shape[0],
+                                     b.shape[1], m, efc, IP if ip else L2, seed, gpu))
+        return cls(h, IP if ip else L2)
+
+    @classmethod
+    def build_device(cls, d_base, n, dim, m, efc, ip=False, seed=1234, d_ids=0, gpu=0):
+        """GPU construction over rows already in HBM (raw device pointers)."""
+        h = C.c_void_p()
+        _check(lib().shn_index_build_device(C.byref(h), d_base, d_ids or None, n, dim, m, efc, IP if ip else L2, seed, gpu))
+        return cls(h, IP if ip else L2)
+
+    def build_stats(self):
+        st = Stats()
+        _check(lib().shn_index_build_stats(self._h, C.byref(st)))
+        return st.as_dict()
 
     def close(self):
         if getattr(self, "_h", None) and _LIB is not None:

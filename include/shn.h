@@ -63,6 +63,19 @@ int shn_index_load(shn_index** out, const char* const* dump_paths, int n_parts, 
 int shn_index_load_mem(shn_index** out, const void* const* dumps, const uint64_t* sizes, int n_parts, uint32_t dim,
                        uint32_t m, shn_metric metric, int gpu_id);
 
+/* Build an index over base[n][dim] (host, row-major fp32; ids[i] = external id of row i, NULL = i) on the GPU.
+ * Replaces ComputeNode::run_inserts -> hnsw::schedule<D,true> -> HNSW::insert (compute_node.cc:322,
+ * hnsw/scheduler.hh:20, hnsw/hnsw.hh:40-251).  Levels are drawn with the reference's recipe
+ * floor(-ln(U)/ln(m)) from mt19937(seed) (hnsw.hh:48,563).  The graph is not the reference's graph (insertion
+ * is batched); it meets the same recall at equal m / ef_construction / ef. */
+int shn_index_build(shn_index** out, const float* base, const uint32_t* ids, uint64_t n, uint32_t dim, uint32_t m,
+                    uint32_t ef_construction, shn_metric metric, uint32_t seed, int gpu_id);
+/* Same with base already in device memory on gpu_id (row stride = dim floats). */
+int shn_index_build_device(shn_index** out, const float* d_base, const uint32_t* d_ids, uint64_t n, uint32_t dim,
+                           uint32_t m, uint32_t ef_construction, shn_metric metric, uint32_t seed, int gpu_id);
+/* Build-time counters (distcomps, processed, kernel_ms) of a handle created by shn_index_build*. */
+int shn_index_build_stats(const shn_index*, shn_stats* out);
+
 /* Write the index as n_parts reference-format dumps (nodes dealt round-robin to parts when n_parts > 1).
  * Replaces MemoryNode::store_or_load_index store branch (memory_node.hh:187-195). */
 int shn_index_store(const shn_index*, const char* const* dump_paths, int n_parts);
@@ -86,7 +99,8 @@ uint32_t shn_index_m(const shn_index*);
 uint32_t shn_index_max_level(const shn_index*);  /* build.max_level in the reference's JSON */
 uint64_t shn_index_hbm_bytes(const shn_index*);  /* device memory held by the handle */
 uint64_t shn_index_dump_bytes(const shn_index*); /* "index_size": bytes the reference would have allocated (rdma_atomics.hh:98) */
-/* Options: "warps_per_sm" (0 = auto): cap on resident query warps per SM.  Distances are always summed in the
+/* Options: "warps_per_sm" (0 = auto): cap on resident query warps per SM; "visited_smem_entries" (0 = auto): size of
+ * the per-warp visited table in shared memory (the rest spills to HBM, still exact).  Distances are always summed in the
  * reference's own order (src/hnsw/distance.hh as compiled, see oracle/hnsw_oracle.c), so results are bit-identical
  * to the reference's except on exact distance ties. */
 int shn_set_option(shn_index*, const char* key, int64_t value);

@@ -1,0 +1,106 @@
+"""GPU construction (shn_index_build): the graph is not the reference's graph (insertion is batched), so the bar is
+(1) structural validity in the reference's dump format — the oracle parses and searches it, bit-identical to the GPU
+search of the same index, (2) the reference's level recipe reproduced exactly, (3) recall parity with an index the
+reference itself built from the same rows at equal M / efC / ef."""
+import numpy as np
+import pytest
+
+import datagen
+import hnsw_oracle
+import shine_ref
+
+pytestmark = pytest.mark.gpu
+
+
+def check_structure(ex, oracle, m):
+    n = len(ex["uid"])
+    assert sorted(ex["uid"].tolist()) == list(range(n))
+    cnt, adj, lvl = ex["l0_cnt"], ex["l0_adj"], ex["level"]
+    assert (cnt <= 2 * m).all() and (n == 1 or (cnt[1:] > 0).any())
+    for r in range(n):
+        nb = adj[r, :cnt[r]]
+        assert (nb < n).all() and (nb != r).all() and len(set(nb.tolist())) == len(nb), f"row {r}"
+    for r in np.nonzero(lvl > 0)[0]:
+        for l in range(1, lvl[r] + 1):
+            nb = oracle.neighbors(int(r), l)
+            assert len(nb) <= m and (lvl[nb] >= l).all() and (nb != r).all() and len(set(nb.tolist())) == len(nb)
+    assert lvl[oracle.entry_row] == lvl.max() == oracle.max_level
+
+
+@pytest.mark.parametrize("n,dim,m,efc,ip", [(3000, 32, 16, 100, False), (2000, 40, 8, 60, True), (1500, 128, 16, 80, False),
+                                            (40, 8, 4, 20, False), (1, 16, 8, 20, False), (700, 96, 32, 64, False)])
+def test_built_index_is_a_valid_reference_dump(pkg, n, dim, m, efc, ip):
+    base, queries = datagen.base_and_queries(n, 64, dim, normalize=ip)
+    with pkg.Index.build(base, m, efc, ip=ip, seed=1234) as ix:
+        assert ix.n == n
+        k = min(10, n)
+        ids, dists, st = ix.search(queries, k, 64)
+        dumps = [d.tobytes() for d in ix.to_dumps(2 if n > 100 else 1)]
+        bs = ix.build_stats()
+        assert bs["processed"] == n and (bs["distcomps"] > 0 or n == 1)
+    oracle = hnsw_oracle.Index(dumps, dim, m)
+    assert oracle.n == n
+    ex = oracle.export()
+    check_structure(ex, oracle, m)
+    assert np.array_equal(ex["vectors"][np.argsort(ex["uid"])], base)
+    oi, od, _, ct = oracle.knn(queries, k, 64, ip=ip, counters=True, track_ties=True)
+    oi, od = hnsw_oracle.sorted_results(oi, od)
+    clean = ct["tie"] == 0
+    assert (oi[clean] == ids[clean]).all() and (od[clean].view(np.uint32) == dists[clean].view(np.uint32)).all()
+    if n >= 1000:
+        gt = datagen.bruteforce(base, queries, 10, ip=ip)
+        assert datagen.recall(ids, gt) >= 0.97
+
+
+def test_levels_follow_the_reference_recipe(pkg):
+    """Same seed, same m: node i gets the level the reference's single-threaded build gives it (hnsw.hh:48,106)."""
+    if not shine_ref.available():
+        pytest.skip("oracle/_ref not built")
+    n, dim, m = 4000, 16, 6
+    base, _ = datagen.base_and_queries(n, 1, dim)
+    ref_dumps, _, _ = shine_ref.build(base, m=m, efc=20, seed=77, threads=1, coroutines=1)
+    ref = hnsw_oracle.Index(ref_dumps, dim, m).export()
+    with pkg.Index.build(base, m, 20, seed=77) as ix:
+        got = hnsw_oracle.Index([d.tobytes() for d in ix.to_dumps(1)], dim, m).export()
+    ref_lvl = ref["level"][np.argsort(ref["uid"])]
+    got_lvl = got["level"][np.argsort(got["uid"])]
+    assert (ref_lvl == got_lvl).all() and ref_lvl.max() >= 3
+
+
+def test_build_is_deterministic(pkg):
+    base, _ = datagen.base_and_queries(5000, 1, 24)
+    with pkg.Index.build(base, 12, 64) as a, pkg.Index.build(base, 12, 64) as b:
+        da, db = a.to_dumps(1)[0], b.to_dumps(1)[0]
+    assert da.tobytes() == db.tobytes()
+
+
+@pytest.mark.parametrize("dim,ip", [(64, False), (48, True)])
+def test_recall_parity_with_reference_built_index(pkg, dim, ip):
+    """Equal M / efC / ef: recall@10 of the GPU-built index vs an index built by the reference's own insert path."""
+    if not shine_ref.available():
+        pytest.skip("oracle/_ref not built")
+    n, m, efc = 30000, 16, 200
+    base, queries = datagen.base_and_queries(n, 1000, dim, normalize=ip)
+    gt = datagen.bruteforce(base, queries, 10, ip=ip)
+    ref_dumps, _, _ = shine_ref.build(base, m=m, efc=efc, ip=ip, threads=8)
+    out = []
+    with pkg.Index.from_dumps(ref_dumps, dim, m, ip=ip) as ref_ix, pkg.Index.build(base, m, efc, ip=ip) as gpu_ix:
+        for ef in (10, 16, 32, 64, 128):
+            r_ref = datagen.recall(ref_ix.search(queries, 10, ef)[0], gt)
+            r_gpu = datagen.recall(gpu_ix.search(queries, 10, ef)[0], gt)
+            out.append((ef, r_ref, r_gpu))
+    print("ef, recall(reference-built), recall(gpu-built):", out)
+    for ef, r_ref, r_gpu in out:
+        assert r_gpu >= r_ref - (0.002 if ef >= 64 else 0.01), out
+
+
+def test_build_argument_errors(pkg):
+    base = np.zeros((10, 8), np.float32)
+    with pytest.raises(pkg.ShnError) as e:
+        pkg.Index.build(base, 1, 10)
+    assert e.value.code == -1
+    with pytest.raises(pkg.ShnError):
+        pkg.Index.build(base, 8, 0)
+    with pkg.Index.build(base, 4, 10) as ix:  # all rows identical (zeros): ties everywhere, must still terminate
+        ids, _, _ = ix.search(base[:2], 5, 10)
+        assert (ids != 0xFFFFFFFF).all()
