@@ -238,7 +238,13 @@ def main():
     batches = [synth_rows(nq, wl["dim"], 2002 + 1000 * rank + b, dev, wl["normalize"]) for b in range(n_batches)]
     ids = torch.empty((nq, K), dtype=torch.int32, device=dev)
     dists = torch.empty((nq, K), dtype=torch.float32, device=dev)
-    stream = torch.cuda.current_stream().cuda_stream
+    # a non-default torch stream: the C ABI launches on the stream it is handed, and torch.cuda.Event only sees
+    # torch's current stream
+    tstream = torch.cuda.Stream(device=dev)
+    torch.cuda.synchronize()
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
+    assert stream != 0
 
     # ---- ef selection: the smallest ef of the sweep with recall@10 >= 0.9 (rank 0 decides) -----------------------
     nrec = min(args.recall_queries, nq)
@@ -299,6 +305,7 @@ def main():
     clocks.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kern_ms = []
+    torch.cuda.profiler.start()  # no-op unless under ncu --profile-from-start off
     ev0.record()
     for i in range(args.steps):
         step_device(args.warmup + i)
@@ -306,6 +313,7 @@ def main():
             dist.all_gather(gathered, ids)  # per-GPU top-k lists -> every rank
     ev1.record()
     barrier()
+    torch.cuda.profiler.stop()
     total_ms = ev0.elapsed_time(ev1)
     clk = clocks.stop()
 
@@ -353,6 +361,9 @@ def main():
         return
 
     traffic = ncu_traffic_bytes()
+    if traffic and not (traffic.get("workload") == args.workload and traffic.get("ef") == ef and
+                        traffic.get("queries_per_launch") == nq):
+        traffic = None  # the committed ncu capture is for another configuration
     line = dict(metric="queries_per_sec at recall@10>=0.9", value=round(value, 1), unit="queries/s", n_gpus=world,
                 steps=args.steps, warmup=args.warmup, ms_per_step=round(total_ms / args.steps, 3), higher_is_better=True,
                 scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
