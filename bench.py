@@ -289,7 +289,10 @@ def main():
         return ix.search_device(batches[i % n_batches].data_ptr(), nq, K, ef, ids.data_ptr(), dists.data_ptr(),
                                 stream=stream, want_stats=False)
 
-    gathered = [torch.empty_like(ids) for _ in range(world)] if dist else None
+    par = pkg.parallel
+
+    def gather():  # per-GPU top-k lists -> every rank, global query order; one all-gather
+        return par.allgather_results(ids, dists, world * nq, rank, world, dist)
 
     def barrier():
         if dist:
@@ -299,7 +302,7 @@ def main():
     for i in range(args.warmup):
         step_device(i)
         if dist:
-            dist.all_gather(gathered, ids)
+            gather()
     barrier()
     clocks = ClockSampler(local_rank)
     clocks.start()
@@ -310,7 +313,7 @@ def main():
     for i in range(args.steps):
         step_device(args.warmup + i)
         if dist:
-            dist.all_gather(gathered, ids)  # per-GPU top-k lists -> every rank
+            gather()
     ev1.record()
     barrier()
     torch.cuda.profiler.stop()

@@ -5,5 +5,5 @@ host/shine_b200; this Python package is only the ctypes binding the tests and be
 The directory name is not an importable identifier: load it with `load_package()` from __graft_entry__.py or
 put this directory on sys.path and `import shn`.
 """
-from . import shn  # noqa: F401
-from .shn import Index, ShnError, build_library, library_path, repartition_dumps  # noqa: F401
+from . import parallel, shn  # noqa: F401
+from .shn import Index, ShnError, build_library, library_path, repartition_dumps, set_build_option  # noqa: F401

@@ -339,6 +339,7 @@ cudaError_t build_graph(BuildJob& job, cudaStream_t stream) {
   const int grid_i_max = occ_i * job.num_sms, grid_l_max = occ_l * job.num_sms;
 
   const uint32_t batch_max = job.batch_max ? job.batch_max : 16384;
+  const uint32_t batch_div = job.batch_div ? job.batch_div : 32;  // a batch is at most 1/batch_div of the graph it is inserted into
   // request slots: (levels linked + 1) * m per new node, laid out per batch
   const std::vector<uint32_t>& level = *job.level_host;
   uint32_t max_levels_sum = 0;
@@ -391,7 +392,7 @@ cudaError_t build_graph(BuildJob& job, cudaStream_t stream) {
     std::vector<uint32_t> req_base_host(batch_max);
     uint32_t inserted = 1;  // the first node is the first entry point (:56-85)
     while (inserted < n) {
-      uint32_t bsz = std::max<uint32_t>(1, inserted / 8);
+      uint32_t bsz = std::max<uint32_t>(1, inserted / batch_div);
       bsz = std::min<uint32_t>(bsz, std::min<uint32_t>(batch_max, n - inserted));
       uint32_t slots = 0;
       uint32_t batch_top = 0, batch_top_node = 0;

@@ -14,6 +14,8 @@ using namespace shn;
 namespace {
 
 thread_local std::string g_err;
+// construction knobs (shn_set_build_option): process-wide, read when shn_index_build* starts
+uint32_t g_build_batch_max = 0, g_build_batch_div = 0;
 
 int fail(int code, const char* fmt, ...) {
   char buf[1024];
@@ -74,7 +76,6 @@ struct shn_index {
   int warps_per_sm = 0;
   uint32_t vis_cap = 0;
   shn_stats build_stats{};
-  uint32_t batch_max = 0;
   bool built = false;
 
   DeviceGraph view() const {
@@ -334,7 +335,7 @@ int shn_index_build_device(shn_index** out, const float* d_base, const uint32_t*
   BuildJob job;
   job.g = ix->view();
   job.l0_w = ix->d_l0; job.up_w = ix->d_up; job.level_dev = ix->d_level; job.level_host = &level;
-  job.n = ix->n; job.efc = ef_construction; job.batch_max = ix->batch_max; job.ip = metric == SHN_IP; job.num_sms = ix->num_sms;
+  job.n = ix->n; job.efc = ef_construction; job.batch_max = g_build_batch_max; job.batch_div = g_build_batch_div; job.ip = metric == SHN_IP; job.num_sms = ix->num_sms;
   cudaError_t e = build_graph(job, s);
   if (e != cudaSuccess) return bail(fail(SHN_ERR_CUDA, "build_graph: %s", cudaGetErrorString(e)));
   if (job.failed) return bail(fail(SHN_ERR_CAPACITY, "%llu inserts overflowed the visited set", job.failed));
@@ -374,6 +375,21 @@ int shn_index_build(shn_index** out, const float* base, const uint32_t* ids, uin
   rc = shn_index_build_device(out, d_base, d_ids, n, dim, m, ef_construction, metric, seed, gpu_id);
   cudaFree(d_base); cudaFree(d_ids);
   return rc;
+}
+
+int shn_set_build_option(const char* key, int64_t value) {
+  if (!key) return fail(SHN_ERR_ARG, "null argument");
+  if (std::strcmp(key, "batch_max") == 0) {
+    if (value < 0 || value > (1 << 20)) return fail(SHN_ERR_ARG, "batch_max must be in [0, 2^20]");
+    g_build_batch_max = static_cast<uint32_t>(value);
+    return SHN_OK;
+  }
+  if (std::strcmp(key, "batch_div") == 0) {
+    if (value < 0 || value > (1 << 20)) return fail(SHN_ERR_ARG, "batch_div must be in [0, 2^20]");
+    g_build_batch_div = static_cast<uint32_t>(value);
+    return SHN_OK;
+  }
+  return fail(SHN_ERR_ARG, "unknown build option '%s'", key);
 }
 
 int shn_index_build_stats(const shn_index* ix, shn_stats* out) {
@@ -450,11 +466,6 @@ int shn_set_option(shn_index* ix, const char* key, int64_t value) {
   if (std::strcmp(key, "warps_per_sm") == 0) {
     if (value < 0 || value > 64) return fail(SHN_ERR_ARG, "warps_per_sm must be in [0, 64]");
     ix->warps_per_sm = static_cast<int>(value);
-    return SHN_OK;
-  }
-  if (std::strcmp(key, "build_batch_max") == 0) {
-    if (value < 0 || value > (1 << 20)) return fail(SHN_ERR_ARG, "build_batch_max must be in [0, 2^20]");
-    ix->batch_max = static_cast<uint32_t>(value);
     return SHN_OK;
   }
   if (std::strcmp(key, "visited_smem_entries") == 0) {

@@ -51,7 +51,7 @@ struct BuildJob {
   uint32_t* up_w = nullptr;
   const uint32_t* level_dev = nullptr;
   const std::vector<uint32_t>* level_host = nullptr;
-  uint32_t n = 0, efc = 0, batch_max = 0;
+  uint32_t n = 0, efc = 0, batch_max = 0, batch_div = 0;
   bool ip = false;
   int num_sms = 0;
   void (*progress)(uint64_t done, uint64_t total) = nullptr;

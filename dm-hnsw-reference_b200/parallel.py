@@ -1,0 +1,49 @@
+"""Host-side logic of the multi-GPU path: one process per GPU (torch.distributed), queries sharded the way the
+reference deals them to compute nodes (round-robin by id, src/io/read_data.hh:58), per-GPU top-k lists exchanged with
+ONE all-gather per batch, recall combined as the reference's rolling recall (compute_node.cc:149-154)."""
+import numpy as np
+import torch
+
+
+def shard_slots(n, rank, world):
+    """Query ids this rank processes: id % world == rank (io/read_data.hh:58)."""
+    return np.arange(rank, n, world, dtype=np.int64)
+
+
+def shard_size(n, rank, world):
+    return (n - rank + world - 1) // world if rank < n else 0
+
+
+def allgather_results(ids, dists, n_total, rank, world, dist=None):
+    """ids [n_local,k] int32, dists [n_local,k] float32 for the slots shard_slots(n_total, rank, world), on any device.
+    Returns ([n_total,k] ids, [n_total,k] dists) in global query order on every rank.  One all-gather (ids and the
+    distance bits travel in one int32 buffer)."""
+    k = ids.shape[1]
+    if world == 1:
+        return ids, dists
+    per = (n_total + world - 1) // world  # ranks with one slot fewer pad the last row
+    send = torch.full((per, 2 * k), -1, dtype=torch.int32, device=ids.device)
+    send[: ids.shape[0], :k] = ids
+    send[: ids.shape[0], k:] = dists.view(torch.int32)
+    recv = torch.empty((world, per, 2 * k), dtype=torch.int32, device=ids.device)
+    dist.all_gather_into_tensor(recv.view(world * per, 2 * k), send)
+    # slot s of rank r is global query r + s*world: [world, per] -> [per, world] -> flatten, cut the padding
+    merged = recv.permute(1, 0, 2).reshape(per * world, 2 * k)[:n_total]
+    return merged[:, :k].contiguous(), merged[:, k:].contiguous().view(torch.float32)
+
+
+def local_recall(ids, gt_rows):
+    """compute_local_recall (compute_node.cc:579-600): hits / (processed * k) against the first k ground-truth ids."""
+    k = ids.shape[1]
+    if ids.shape[0] == 0:
+        return 0.0
+    hit = (ids.long()[:, :, None] == gt_rows[:, None, :k].long()).any(2).sum().item()
+    return hit / (ids.shape[0] * k)
+
+
+def rolling_recall(recall_local, processed_local, n_total, dist=None, device="cpu"):
+    """sum_i recall_i * processed_i / total (compute_node.cc:149-154, statistics.hh combine())."""
+    t = torch.tensor([recall_local * processed_local / max(n_total, 1)], dtype=torch.float64, device=device)
+    if dist is not None:
+        dist.all_reduce(t)
+    return float(t.item())

@@ -67,6 +67,7 @@ def lib():
                                       C.c_uint32, C.c_int, C.c_uint32, C.c_int]
         L.shn_index_build_device.argtypes = L.shn_index_build.argtypes
         L.shn_index_build_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
+        L.shn_set_build_option.argtypes = [C.c_char_p, C.c_int64]
         L.shn_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int64]
         L.shn_search.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p,
                                  C.POINTER(Stats)]
@@ -215,3 +216,7 @@ def repartition_dumps(dumps, dim, m, n_parts_out):
     optrs = (C.c_void_p * n_parts_out)(*[b.ctypes.data for b in out])
     _check(lib().shn_dump_repartition(ptrs, sizes, len(bufs), dim, m, n_parts_out, optrs, osz))
     return out
+
+
+def set_build_option(key, value):
+    _check(lib().shn_set_build_option(key.encode(), int(value)))

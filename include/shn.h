@@ -73,6 +73,9 @@ int shn_index_build(shn_index** out, const float* base, const uint32_t* ids, uin
 /* Same with base already in device memory on gpu_id (row stride = dim floats). */
 int shn_index_build_device(shn_index** out, const float* d_base, const uint32_t* d_ids, uint64_t n, uint32_t dim,
                            uint32_t m, uint32_t ef_construction, shn_metric metric, uint32_t seed, int gpu_id);
+/* Construction knobs, process-wide, read when shn_index_build* starts: "batch_max" (nodes inserted per step, default
+ * 16384) and "batch_div" (a step inserts at most 1/batch_div of the current graph, default 32); 0 = default. */
+int shn_set_build_option(const char* key, int64_t value);
 /* Build-time counters (distcomps, processed, kernel_ms) of a handle created by shn_index_build*. */
 int shn_index_build_stats(const shn_index*, shn_stats* out);
 
