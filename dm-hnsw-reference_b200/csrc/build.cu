@@ -9,7 +9,7 @@
 //   2. the requests are sorted by (level, target, source) — a radix sort, so the result is deterministic;
 //   3. link_kernel — one warp per (level, target): append the new sources if the list has room, otherwise re-run the
 //      heuristic over old + new neighbours with distances to the target (:180-225).
-// Nodes of one batch do not see each other; batches grow with the graph (at most 1/8 of it) so this stays a small
+// Nodes of one batch do not see each other; batches grow with the graph (at most 1/64 of it) so this stays a small
 // perturbation.  The graph is therefore not the reference's graph — the bar is equal recall at equal M / efC / ef
 // (tests/test_build.py) — but every distance is computed in the reference's arithmetic and the selection rule is
 // the reference's, and the result is written in the reference's dump format by shn_index_store.
@@ -339,7 +339,7 @@ cudaError_t build_graph(BuildJob& job, cudaStream_t stream) {
   const int grid_i_max = occ_i * job.num_sms, grid_l_max = occ_l * job.num_sms;
 
   const uint32_t batch_max = job.batch_max ? job.batch_max : 16384;
-  const uint32_t batch_div = job.batch_div ? job.batch_div : 32;  // a batch is at most 1/batch_div of the graph it is inserted into
+  const uint32_t batch_div = job.batch_div ? job.batch_div : 64;  // a batch is at most 1/batch_div of the graph it is inserted into
   // request slots: (levels linked + 1) * m per new node, laid out per batch
   const std::vector<uint32_t>& level = *job.level_host;
   uint32_t max_levels_sum = 0;
