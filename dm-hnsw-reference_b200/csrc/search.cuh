@@ -14,6 +14,12 @@
 
 namespace shn {
 
+#ifndef SHN_STEP
+#define SHN_STEP 8
+#endif
+#ifndef SHN_GSTEP
+#define SHN_GSTEP 4
+#endif
 constexpr uint32_t kFull = 0xFFFFFFFFu;
 constexpr uint32_t kExpanded = 0x80000000u;  // flag bit in a queue entry's row id
 constexpr int kMaxList = 64;                  // 2m <= 64
@@ -84,8 +90,13 @@ __device__ __forceinline__ float finish_row(float s0, float s1, float s2, float 
 // dist(query, row) for rows s_rows[0..cnt) -> s_out[0..cnt).  s_q: the query in shared memory (16-byte aligned,
 // dim floats).  NCHUNK > 0: dim == 16*NCHUNK known at compile time (fully unrolled, all loads of a pass in flight);
 // NCHUNK == 0: any dim.
+#ifdef SHN_EVAL_NOINLINE
+#define SHN_EVAL_ATTR __noinline__
+#else
+#define SHN_EVAL_ATTR __forceinline__
+#endif
 template <bool IP, int NCHUNK>
-__device__ __forceinline__ void eval_rows(const DeviceGraph& g, const float* s_q, const uint32_t* s_rows, uint32_t cnt,
+__device__ SHN_EVAL_ATTR void eval_rows(const DeviceGraph& g, const float* s_q, const uint32_t* s_rows, uint32_t cnt,
                                           float* s_out, int lane) {
   const int h = lane & 1;
   const float4* s_q4 = reinterpret_cast<const float4*>(s_q);
@@ -96,7 +107,7 @@ __device__ __forceinline__ void eval_rows(const DeviceGraph& g, const float* s_q
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
     if (NCHUNK > 0) {
       constexpr int NC = NCHUNK > 0 ? NCHUNK : 1;
-      constexpr int STEP = NC < 8 ? NC : 8;  // chunks per wave of loads (2 loads each)
+      constexpr int STEP = NC < SHN_STEP ? NC : SHN_STEP;  // chunks per wave of loads (2 loads each)
 #pragma unroll
       for (int c0 = 0; c0 < NC; c0 += STEP) {
         float4 a[STEP], b[STEP];
@@ -114,17 +125,17 @@ __device__ __forceinline__ void eval_rows(const DeviceGraph& g, const float* s_q
       }
     } else {
       const uint32_t nchunk = g.dim >> 4;
-      for (uint32_t c0 = 0; c0 < nchunk; c0 += 4) {
-        float4 a[4], b[4];
+      for (uint32_t c0 = 0; c0 < nchunk; c0 += SHN_GSTEP) {
+        float4 a[SHN_GSTEP], b[SHN_GSTEP];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < SHN_GSTEP; ++c) {
           if (c0 + c < nchunk) {
             a[c] = ldg_f4(rp + (c0 + c) * 4 + h);
             b[c] = ldg_f4(rp + (c0 + c) * 4 + 2 + h);
           }
         }
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < SHN_GSTEP; ++c) {
           if (c0 + c < nchunk) chunk_accumulate<IP>(s_q4[(c0 + c) * 4 + h], s_q4[(c0 + c) * 4 + 2 + h], a[c], b[c], s0, s1, s2, s3);
         }
       }
@@ -273,30 +284,47 @@ __device__ __forceinline__ void visited_reset(VisitedSet& v, int lane) {
   __syncwarp();
 }
 
+// One 128-bit shared-memory read that the compiler may not cache across the CAS of another lane.
+__device__ __forceinline__ uint4 lds_bucket(const uint32_t* p) {
+  uint4 k;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(k.x), "=r"(k.y), "=r"(k.z), "=r"(k.w)
+               : "r"(static_cast<uint32_t>(__cvta_generic_to_shared(p)))
+               : "memory");
+  return k;
+}
+
 // Each lane with active==true offers one id (ids offered together are distinct); returns true for lanes whose
-// id was not in the set (and now is).
+// id was not in the set (and now is).  The shared table is organised in 16-byte buckets of four keys: one 128-bit
+// read answers "already visited" (about half of all offers) without an atomic, an insert costs that read plus one
+// CAS on the first free slot of the bucket.
 __device__ __forceinline__ bool visited_test_and_set(VisitedSet& v, uint32_t id, bool active, int lane) {
   bool is_new = false;
+  const uint32_t nbuckets = v.cap >> 2;
   if (v.count + 32 <= v.limit) {  // warp-uniform: room for every lane
     if (active) {
-      uint32_t s = hash_row(id) & (v.cap - 1);
+      uint32_t b = hash_row(id) & (nbuckets - 1);
       for (;;) {
-        const uint32_t old = atomicCAS(&v.tab[s], kInvalid, id);
+        const uint4 k = lds_bucket(v.tab + 4 * b);
+        if (k.x == id || k.y == id || k.z == id || k.w == id) break;
+        const int e = k.x == kInvalid ? 0 : (k.y == kInvalid ? 1 : (k.z == kInvalid ? 2 : (k.w == kInvalid ? 3 : -1)));
+        if (e < 0) { b = (b + 1) & (nbuckets - 1); continue; }
+        const uint32_t old = atomicCAS(&v.tab[4 * b + e], kInvalid, id);
         if (old == kInvalid) { is_new = true; break; }
         if (old == id) break;
-        s = (s + 1) & (v.cap - 1);
+        // another lane took the slot: look at the same bucket again
       }
     }
     v.count += __popc(__ballot_sync(kFull, is_new));
   } else {
     bool found = false;
     if (active) {  // the shared table is closed for inserts but still answers lookups
-      uint32_t s = hash_row(id) & (v.cap - 1);
+      uint32_t b = hash_row(id) & (nbuckets - 1);
       for (;;) {
-        const uint32_t old = v.tab[s];
-        if (old == kInvalid) break;
-        if (old == id) { found = true; break; }
-        s = (s + 1) & (v.cap - 1);
+        const uint4 k = reinterpret_cast<const uint4*>(v.tab)[b];
+        if (k.x == id || k.y == id || k.z == id || k.w == id) { found = true; break; }
+        if (k.w == kInvalid) break;  // buckets fill front to back: a free last slot ends the probe sequence
+        b = (b + 1) & (nbuckets - 1);
       }
     }
     if (v.ovf_count + 32 > v.ovf_limit) {
@@ -329,6 +357,11 @@ __device__ __forceinline__ void beam_search(const DeviceGraph& g, const float* s
                                             uint32_t& c_dist, uint32_t& c_vis, uint32_t& c_lists, int lane) {
   const uint32_t width = level == 0 ? g.m0 : g.m;
   uint32_t lb = 0;  // every entry below lb is expanded
+  // The list of the entry most likely to be expanded NEXT (the closest unexpanded one after the current candidate)
+  // is loaded while the current candidate's rows are in flight; if the merge does not put a closer entry in front
+  // of it, the next iteration starts with its list already in registers (one dependent HBM round trip per
+  // expansion instead of two).  Purely a load-scheduling device: what is expanded, and in which order, is unchanged.
+  uint32_t pre_row = kInvalid, pre0 = kInvalid, pre1 = kInvalid;
   for (;;) {
     // next_candidates.pop(): the closest entry not yet expanded
     uint32_t pos = kInvalid;
@@ -345,16 +378,48 @@ __device__ __forceinline__ void beam_search(const DeviceGraph& g, const float* s
     lb = pos + 1;
     ++c_lists;
 
-    // read_neighborlist + the visited filter, in stored order (:437-443)
-    const uint32_t* list = level == 0 ? g.l0 + static_cast<size_t>(cand) * g.m0
-                                      : g.up + (static_cast<size_t>(__ldg(g.up_base + cand)) + (level - 1)) * g.m;
+    // read_neighborlist (:437): from the registers filled during the previous expansion, or from HBM
+    uint32_t nb0, nb1 = kInvalid;
+    if (cand == pre_row) {
+      nb0 = pre0; nb1 = pre1;
+    } else {
+      const uint32_t* list = level == 0 ? g.l0 + static_cast<size_t>(cand) * g.m0
+                                        : g.up + (static_cast<size_t>(__ldg(g.up_base + cand)) + (level - 1)) * g.m;
+      nb0 = static_cast<uint32_t>(lane) < width ? __ldg(list + lane) : kInvalid;
+      if (width > 32) nb1 = static_cast<uint32_t>(lane) + 32 < width ? __ldg(list + lane + 32) : kInvalid;
+    }
+#ifndef SHN_NO_LIST_PREFETCH
+    {
+      uint32_t pos2 = kInvalid;
+      for (uint32_t b = lb & ~31u; b < qsize; b += 32) {
+        const uint32_t j = b + lane;
+        const bool un = j < qsize && j >= lb && !(qi[j] & kExpanded);
+        const uint32_t mask = __ballot_sync(kFull, un);
+        if (mask) { pos2 = b + __ffs(mask) - 1; break; }
+      }
+      pre_row = kInvalid;
+      if (pos2 != kInvalid) {
+        pre_row = qi[pos2];
+        const uint32_t* list = level == 0 ? g.l0 + static_cast<size_t>(pre_row) * g.m0
+                                          : g.up + (static_cast<size_t>(__ldg(g.up_base + pre_row)) + (level - 1)) * g.m;
+        pre0 = static_cast<uint32_t>(lane) < width ? __ldg(list + lane) : kInvalid;
+        if (width > 32) pre1 = static_cast<uint32_t>(lane) + 32 < width ? __ldg(list + lane + 32) : kInvalid;
+      }
+    }
+#endif
+
+    // the visited filter, in stored order (:440-443)
     uint32_t cnt = 0;
-    for (uint32_t j0 = 0; j0 < width; j0 += 32) {
-      const uint32_t j = j0 + lane;
-      const uint32_t nb = j < width ? __ldg(list + j) : kInvalid;
-      const bool fresh = visited_test_and_set(vis, nb, nb != kInvalid, lane);
+    {
+      const bool fresh = visited_test_and_set(vis, nb0, nb0 != kInvalid, lane);
       const uint32_t mask = __ballot_sync(kFull, fresh);
-      if (fresh) s_rows[cnt + __popc(mask & ((1u << lane) - 1))] = nb;
+      if (fresh) s_rows[__popc(mask & ((1u << lane) - 1))] = nb0;
+      cnt = __popc(mask);
+    }
+    if (width > 32) {
+      const bool fresh = visited_test_and_set(vis, nb1, nb1 != kInvalid, lane);
+      const uint32_t mask = __ballot_sync(kFull, fresh);
+      if (fresh) s_rows[cnt + __popc(mask & ((1u << lane) - 1))] = nb1;
       cnt += __popc(mask);
     }
     __syncwarp();

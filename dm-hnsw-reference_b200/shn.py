@@ -30,7 +30,7 @@ class Stats(C.Structure):
 
 
 def library_path():
-    return os.path.join(_HERE, "libshn_b200.so")
+    return os.environ.get("SHN_LIB") or os.path.join(_HERE, "libshn_b200.so")
 
 
 def build_library():

@@ -8,21 +8,22 @@ import __graft_entry__ as ge
 import bench
 
 n = int(sys.argv[1]); dim = int(sys.argv[2]); nq = int(sys.argv[3]); efc = int(sys.argv[4]) if len(sys.argv) > 4 else 200
-bmax = int(sys.argv[5]) if len(sys.argv) > 5 else 0
+ip = len(sys.argv) > 5 and sys.argv[5] == "ip"
+efs = [int(x) for x in sys.argv[6].split(",")] if len(sys.argv) > 6 else [16, 32, 64, 128, 256]
 pkg = ge.load_package()
 dev = torch.device("cuda")
-base = bench.synth_rows(n, dim, 1001, dev)
-q = bench.synth_rows(nq, dim, 2002, dev)
+base = bench.synth_rows(n, dim, 1001, dev, normalize=ip)
+q = bench.synth_rows(nq, dim, 2002, dev, normalize=ip)
 torch.cuda.synchronize()
 t = time.time()
-ix = pkg.Index.build_device(base.data_ptr(), n, dim, 16, efc)
+ix = pkg.Index.build_device(base.data_ptr(), n, dim, 16, efc, ip=ip)
 bs = ix.build_stats()
 print(f"build n={n} dim={dim} efc={efc}: {time.time() - t:.1f}s wall, {bs['kernel_ms'] / 1e3:.1f}s device, "
       f"{n / bs['kernel_ms'] * 1e3 / 1e3:.1f}k inserts/s, distcomps/insert {bs['distcomps'] / n:.0f}, max_level {ix.max_level}", flush=True)
-gt = bench.ground_truth(base, q[:5000], 10, False)
+gt = bench.ground_truth(base, q[:5000], 10, ip)
 ids = torch.empty((nq, 10), dtype=torch.int32, device=dev)
 dists = torch.empty((nq, 10), dtype=torch.float32, device=dev)
-for ef in (16, 32, 64, 128, 256):
+for ef in efs:
     ix.search_device(q.data_ptr(), nq, 10, ef, ids.data_ptr(), dists.data_ptr())
     best = 1e9
     for _ in range(3):
