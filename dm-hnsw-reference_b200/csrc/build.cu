@@ -78,7 +78,7 @@ __device__ __forceinline__ uint32_t select_neighbors(const DeviceGraph& g, const
     const float dc = c_dist[ci];
     for (uint32_t f = lane; f < g.row_f4; f += 32) s_c4[f] = ldg_f4(g.vec + static_cast<size_t>(row) * g.row_f4 + f);
     __syncwarp();
-    eval_rows<IP, NCHUNK>(g, s_c, sel_rows, ns, s_tmp, lane);
+    eval_rows<IP, NCHUNK, SHN_SMALL_PASSES>(g, s_c, sel_rows, ns, s_tmp, lane);
     bool closer = false;
     for (uint32_t j = lane; j < ns; j += 32) closer |= s_tmp[j] < dc;  // :506
     distcomps += ns;
@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(kBuildWarps * 32, 4) insert_search_kernel(cons
     if (lane == 0) s_rows[0] = g.ep_row;
     __syncwarp();
     uint32_t c_dist = 0, c_vis = 0, c_lists = 0;
-    eval_rows<IP, NCHUNK>(g, s_q, s_rows, 1, s_dist, lane);
+    eval_rows<IP, NCHUNK, SHN_SMALL_PASSES>(g, s_q, s_rows, 1, s_dist, lane);
     uint32_t cur = g.ep_row;
     float closest = s_dist[0];
     ++c_dist;
@@ -243,7 +243,7 @@ __global__ void __launch_bounds__(kBuildWarps * 32, 4) link_kernel(const BuildPa
     float4* s_q4 = reinterpret_cast<float4*>(s_q);
     for (uint32_t f = lane; f < g.row_f4; f += 32) s_q4[f] = ldg_f4(g.vec + static_cast<size_t>(target) * g.row_f4 + f);
     __syncwarp();
-    eval_rows<IP, NCHUNK>(g, s_q, raw_rows, cnt_old, raw_dist, lane);
+    eval_rows<IP, NCHUNK, SHN_SMALL_PASSES>(g, s_q, raw_rows, cnt_old, raw_dist, lane);
     t_dist += cnt_old;
     for (uint32_t i = lane; i < gsz; i += 32) {
       raw_rows[cnt_old + i] = static_cast<uint32_t>(p.req_key[r + i] & kMask30);
@@ -292,9 +292,10 @@ cudaError_t setup_t(size_t smem_insert, size_t smem_link, int* occ_insert, int* 
   return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ_link, link_kernel<IP, NCHUNK>, kBuildWarps * 32, smem_link);
 }
 
-#define DISPATCH(fn, ip, v, ...)                                                                         \
-  ((ip) ? ((v) == 8 ? fn<true, 8>(__VA_ARGS__) : (v) == 6 ? fn<true, 6>(__VA_ARGS__) : fn<true, 0>(__VA_ARGS__)) \
-        : ((v) == 8 ? fn<false, 8>(__VA_ARGS__) : (v) == 6 ? fn<false, 6>(__VA_ARGS__) : fn<false, 0>(__VA_ARGS__)))
+#define DISPATCH_V(fn, ip, v, ...)                                                                   \
+  ((v) == 128 ? fn<ip, 128>(__VA_ARGS__) : (v) == 96 ? fn<ip, 96>(__VA_ARGS__) : (v) == 200 ? fn<ip, 200>(__VA_ARGS__) \
+   : (v) == 960 ? fn<ip, 960>(__VA_ARGS__) : fn<ip, 0>(__VA_ARGS__))
+#define DISPATCH(fn, ip, v, ...) ((ip) ? DISPATCH_V(fn, true, v, __VA_ARGS__) : DISPATCH_V(fn, false, v, __VA_ARGS__))
 
 uint32_t next_pow2(uint32_t v) {
   uint32_t p = 1;
@@ -324,7 +325,8 @@ void draw_levels(uint64_t n, uint32_t m, uint32_t seed, std::vector<uint32_t>& l
 cudaError_t build_graph(BuildJob& job, cudaStream_t stream) {
   const uint32_t n = job.n, m = job.g.m;
   const bool ip = job.ip;
-  const int v = job.g.dim == 128 ? 8 : (job.g.dim == 96 ? 6 : 0);
+  const uint32_t d_rt = job.g.dim;
+  const int v = (d_rt == 96 || d_rt == 128 || d_rt == 200 || d_rt == 960) ? static_cast<int>(d_rt) : 0;
   const uint32_t q_floats = job.g.row_f4 * 4;
   const uint32_t ef_cap = (job.efc + 31u) & ~31u;
   uint32_t vis_cap = next_pow2(std::min<uint32_t>(std::max<uint32_t>(job.efc * 12u, 1024u), 4096u));

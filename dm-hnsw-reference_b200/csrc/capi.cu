@@ -108,7 +108,7 @@ int select_device(int gpu_id, int* num_sms) {
 int upload(shn_index* ix, const HostGraph& g) {
   ix->n = g.n; ix->dim = g.dim; ix->m = g.m; ix->ep_row = g.ep_row; ix->max_level = g.max_level; ix->n_up = g.n_up;
   ix->max_level_of_ep = g.level[g.ep_row];
-  ix->row_f4 = ((g.dim + 3) / 4 + 1) & ~1u;  // whole 32-byte sectors per row
+  ix->row_f4 = row_stride_f4(g.dim);
   const size_t row_floats = static_cast<size_t>(ix->row_f4) * 4;
   const size_t m0 = 2ull * g.m;
   CU(cudaMalloc(&ix->d_vec, g.n * row_floats * sizeof(float)));
@@ -118,12 +118,18 @@ int upload(shn_index* ix, const HostGraph& g) {
   CU(cudaMalloc(&ix->d_ext_id, g.n * sizeof(uint32_t)));
   CU(cudaMalloc(&ix->d_level, g.n * sizeof(uint32_t)));
   ix->hbm_bytes = g.n * (row_floats * 4 + m0 * 4 + 12) + std::max<size_t>(g.n_up, 1) * g.m * 4;
-  if (row_floats == g.dim) {
-    CU(cudaMemcpyAsync(ix->d_vec, g.vec.data(), g.n * row_floats * sizeof(float), cudaMemcpyHostToDevice, ix->stream));
-  } else {
-    CU(cudaMemsetAsync(ix->d_vec, 0, g.n * row_floats * sizeof(float), ix->stream));
-    CU(cudaMemcpy2DAsync(ix->d_vec, row_floats * sizeof(float), g.vec.data(), g.dim * sizeof(float), g.dim * sizeof(float),
-                         g.n, cudaMemcpyHostToDevice, ix->stream));
+  {  // components: natural order on the host -> stored order in HBM, in slabs through a staging buffer
+    const uint64_t slab = std::min<uint64_t>(g.n, 1u << 20);
+    float* stage = nullptr;
+    CU(cudaMalloc(&stage, slab * g.dim * sizeof(float)));
+    for (uint64_t r0 = 0; r0 < g.n; r0 += slab) {
+      const uint64_t cnt = std::min<uint64_t>(slab, g.n - r0);
+      cudaError_t e = cudaMemcpyAsync(stage, g.vec.data() + r0 * g.dim, cnt * g.dim * sizeof(float), cudaMemcpyHostToDevice, ix->stream);
+      if (e == cudaSuccess) e = rows_to_layout(stage, reinterpret_cast<float*>(ix->d_vec) + r0 * row_floats, cnt, g.dim, ix->row_f4, ix->stream);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(ix->stream);
+      if (e != cudaSuccess) { cudaFree(stage); return fail(SHN_ERR_CUDA, "uploading components: %s", cudaGetErrorString(e)); }
+    }
+    cudaFree(stage);
   }
   CU(cudaMemcpyAsync(ix->d_l0, g.l0.data(), g.n * m0 * sizeof(uint32_t), cudaMemcpyHostToDevice, ix->stream));
   CU(cudaMemcpyAsync(ix->d_up_base, g.up_base.data(), g.n * sizeof(uint32_t), cudaMemcpyHostToDevice, ix->stream));
@@ -147,8 +153,19 @@ int download(const shn_index* ix, HostGraph& g) {
   g.up.resize(g.n_up * g.m);
   CU(cudaSetDevice(ix->gpu));
   CU(cudaStreamSynchronize(ix->stream));
-  CU(cudaMemcpy2D(g.vec.data(), g.dim * sizeof(float), ix->d_vec, row_floats * sizeof(float), g.dim * sizeof(float), g.n,
-                  cudaMemcpyDeviceToHost));
+  {
+    const uint64_t slab = std::min<uint64_t>(g.n, 1u << 20);
+    float* stage = nullptr;
+    CU(cudaMalloc(&stage, slab * g.dim * sizeof(float)));
+    for (uint64_t r0 = 0; r0 < g.n; r0 += slab) {
+      const uint64_t cnt = std::min<uint64_t>(slab, g.n - r0);
+      cudaError_t e = rows_from_layout(reinterpret_cast<const float*>(ix->d_vec) + r0 * row_floats, stage, cnt, g.dim, ix->row_f4, ix->stream);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(g.vec.data() + r0 * g.dim, stage, cnt * g.dim * sizeof(float), cudaMemcpyDeviceToHost, ix->stream);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(ix->stream);
+      if (e != cudaSuccess) { cudaFree(stage); return fail(SHN_ERR_CUDA, "downloading components: %s", cudaGetErrorString(e)); }
+    }
+    cudaFree(stage);
+  }
   CU(cudaMemcpy(g.l0.data(), ix->d_l0, g.n * m0 * sizeof(uint32_t), cudaMemcpyDeviceToHost));
   CU(cudaMemcpy(g.up_base.data(), ix->d_up_base, g.n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
   if (g.n_up) CU(cudaMemcpy(g.up.data(), ix->d_up, g.n_up * g.m * sizeof(uint32_t), cudaMemcpyDeviceToHost));
@@ -306,7 +323,7 @@ int shn_index_build_device(shn_index** out, const float* d_base, const uint32_t*
     max_level = std::max(max_level, level[i]);
   }
   ix->n = static_cast<uint32_t>(n); ix->dim = dim; ix->m = m; ix->n_up = n_up; ix->max_level = max_level;
-  ix->row_f4 = ((dim + 3) / 4 + 1) & ~1u;
+  ix->row_f4 = row_stride_f4(dim);
   const size_t row_floats = static_cast<size_t>(ix->row_f4) * 4, m0 = 2ull * m;
   CUB(cudaMalloc(&ix->d_vec, n * row_floats * sizeof(float)));
   CUB(cudaMalloc(&ix->d_l0, n * m0 * sizeof(uint32_t)));
@@ -317,9 +334,7 @@ int shn_index_build_device(shn_index** out, const float* d_base, const uint32_t*
   ix->hbm_bytes = n * (row_floats * 4 + m0 * 4 + 12) + std::max<size_t>(n_up, 1) * m * 4;
   cudaStream_t s = ix->stream;
   CUB(cudaEventRecord(ix->ev[0], s));
-  if (row_floats != dim) CUB(cudaMemsetAsync(ix->d_vec, 0, n * row_floats * sizeof(float), s));
-  CUB(cudaMemcpy2DAsync(ix->d_vec, row_floats * sizeof(float), d_base, dim * sizeof(float), dim * sizeof(float), n,
-                        cudaMemcpyDeviceToDevice, s));
+  CUB(rows_to_layout(d_base, reinterpret_cast<float*>(ix->d_vec), n, dim, ix->row_f4, s));
   CUB(cudaMemsetAsync(ix->d_l0, 0xFF, n * m0 * sizeof(uint32_t), s));
   CUB(cudaMemsetAsync(ix->d_up, 0xFF, std::max<size_t>(n_up, 1) * m * sizeof(uint32_t), s));
   CUB(cudaMemcpyAsync(ix->d_up_base, up_base.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, s));

@@ -4,7 +4,7 @@
 // src/node/node.hh:10-19) addressed by 64-bit RemotePtrs.  That layout is hostile to a GPU (8-byte pointers at
 // 4-byte alignment, variable stride), so nodes are renumbered to dense rows in dump-scan order and stored SoA:
 //
-//   vec      [n][row_f4] float4   components, row padded to 32 B so a row is whole sectors
+//   vec      [n][row_f4] float4   components in the blocked order of row_pos() below, row stride a multiple of 128 B
 //   l0       [n][2m]     u32      level-0 neighbour rows, 0xFFFFFFFF-padded (m=16: exactly one 128 B line)
 //   up_base  [n]         u32      first row of the node's upper lists in `up`, 0xFFFFFFFF when level == 0
 //   up       [n_up][m]   u32      upper lists; the list of level l (>=1) is row up_base + (l-1)
@@ -28,6 +28,25 @@ inline uint64_t ref_alloc_bytes(uint32_t dim, uint32_t m, uint32_t level) {
   uint64_t s = ref_node_bytes(dim) + ref_list0_bytes(m) + level * ref_listu_bytes(m);
   while (s % 8 != 0) s += 4;
   return s;
+}
+
+// Stored order of a row's components ("AVX-lane-major blocks", see search.cuh): the 16*(dim/16) leading elements are
+// grouped in blocks of 32 floats = two 16-element chunks of the reference's distance loop (distance.hh:88-110); inside
+// a block the 16-byte piece t (0..7) holds {v[t], v[8+t], v[16+t], v[24+t]} — everything AVX lane t needs from the two
+// chunks.  An odd last chunk fills half of its block (the rest is zero).  The dim%16 tail elements follow in natural
+// order.  The row stride is rounded up to whole 128-byte lines.
+#ifdef __CUDACC__
+#define SHN_HD __host__ __device__
+#else
+#define SHN_HD
+#endif
+SHN_HD inline uint32_t row_blocks(uint32_t dim) { return ((dim >> 4) + 1) >> 1; }
+SHN_HD inline uint32_t row_stride_f4(uint32_t dim) { return ((32u * row_blocks(dim) + (dim & 15u) + 31u) / 32u) * 8u; }
+SHN_HD inline uint32_t row_pos(uint32_t dim, uint32_t e) {
+  const uint32_t d16 = dim & ~15u;
+  if (e >= d16) return 32u * row_blocks(dim) + (e - d16);
+  const uint32_t w = e & 31u;
+  return (e & ~31u) + 4u * (w & 7u) + (w >> 3);
 }
 
 struct HostGraph {

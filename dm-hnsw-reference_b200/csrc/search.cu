@@ -16,7 +16,7 @@ namespace shn {
 namespace {
 
 #ifndef SHN_MIN_BLOCKS
-#define SHN_MIN_BLOCKS 4
+#define SHN_MIN_BLOCKS 5
 #endif
 constexpr int kWarpsPerBlock = 4;
 
@@ -69,7 +69,9 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, SHN_MIN_BLOCKS) search_ke
 
     // stage the query (database slot components, io/database.hh:17-21)
     const float* gq = p.queries + static_cast<size_t>(q) * g.dim;
-    for (uint32_t j = lane; j < p.q_floats; j += 32) s_q[j] = j < g.dim ? __ldg(gq + j) : 0.f;
+    for (uint32_t j = lane; j < p.q_floats; j += 32) s_q[j] = 0.f;
+    __syncwarp();
+    for (uint32_t j = lane; j < g.dim; j += 32) s_q[row_pos(g.dim, j)] = __ldg(gq + j);  // stored order (graph.h)
     visited_reset(vis, lane);
 
     uint32_t c_dist = 0, c_vup = 0, c_vl0 = 0, c_l0 = 0, c_lup = 0;
@@ -79,7 +81,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, SHN_MIN_BLOCKS) search_ke
     if (g.ep_level > 0) ++c_vup; else ++c_vl0;
     if (lane == 0) s_rows[0] = cur;
     __syncwarp();
-    eval_rows<IP, NCHUNK>(g, s_q, s_rows, 1, s_dist, lane);
+    eval_rows<IP, NCHUNK, SHN_SMALL_PASSES>(g, s_q, s_rows, 1, s_dist, lane);
     float closest = s_dist[0];
     ++c_dist;
     __syncwarp();
@@ -156,7 +158,11 @@ cudaError_t occupancy_t(size_t smem, int* blocks) {
   return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, search_kernel<IP, NCHUNK>, kWarpsPerBlock * 32, smem);
 }
 
-int chunk_variant(uint32_t dim) { return dim == 128 ? 8 : (dim == 96 ? 6 : 0); }
+// dimensions the kernels are instantiated for at compile time (0 = any dim)
+int chunk_variant(uint32_t dim) { return (dim == 96 || dim == 128 || dim == 200 || dim == 960) ? static_cast<int>(dim) : 0; }
+#define DISPATCH_V(fn, ip, v, ...)                                                                   \
+  ((v) == 128 ? fn<ip, 128>(__VA_ARGS__) : (v) == 96 ? fn<ip, 96>(__VA_ARGS__) : (v) == 200 ? fn<ip, 200>(__VA_ARGS__) \
+   : (v) == 960 ? fn<ip, 960>(__VA_ARGS__) : fn<ip, 0>(__VA_ARGS__))
 
 }  // namespace
 
@@ -174,8 +180,8 @@ cudaError_t search_plan(const DeviceGraph& g, const SearchConfig& cfg, uint32_t 
   int blocks = 0;
   cudaError_t e;
   const int v = chunk_variant(g.dim);
-  if (cfg.ip) e = v == 8 ? occupancy_t<true, 8>(bytes, &blocks) : v == 6 ? occupancy_t<true, 6>(bytes, &blocks) : occupancy_t<true, 0>(bytes, &blocks);
-  else        e = v == 8 ? occupancy_t<false, 8>(bytes, &blocks) : v == 6 ? occupancy_t<false, 6>(bytes, &blocks) : occupancy_t<false, 0>(bytes, &blocks);
+  if (cfg.ip) e = DISPATCH_V(occupancy_t, true, v, bytes, &blocks);
+  else        e = DISPATCH_V(occupancy_t, false, v, bytes, &blocks);
   if (e != cudaSuccess) return e;
   if (blocks < 1) return cudaErrorInvalidConfiguration;
   if (cfg.warps_per_sm > 0) {
@@ -218,8 +224,8 @@ cudaError_t search_launch(const DeviceGraph& g, const SearchConfig& cfg, const f
   if (e != cudaSuccess) return e;
 
   const int v = chunk_variant(g.dim);
-  if (cfg.ip) return v == 8 ? launch_t<true, 8>(p, grid, smem, stream) : v == 6 ? launch_t<true, 6>(p, grid, smem, stream) : launch_t<true, 0>(p, grid, smem, stream);
-  return v == 8 ? launch_t<false, 8>(p, grid, smem, stream) : v == 6 ? launch_t<false, 6>(p, grid, smem, stream) : launch_t<false, 0>(p, grid, smem, stream);
+  if (cfg.ip) return DISPATCH_V(launch_t, true, v, p, grid, smem, stream);
+  return DISPATCH_V(launch_t, false, v, p, grid, smem, stream);
 }
 
 }  // namespace shn

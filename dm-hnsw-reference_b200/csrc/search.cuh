@@ -31,117 +31,154 @@ __device__ __forceinline__ float4 ldg_f4(const float4* p) { return __ldg(p); }
 // order was read off the reference build).  The reference accumulates 8 AVX lanes j over 16-element chunks c:
 //   L2:  S_j += fma(d0_j, d0_j, d1_j * d1_j)      d0 = q[16c+j] - v[16c+j],  d1 = q[16c+8+j] - v[16c+8+j]
 //   IP:  S_j += fma(q[16c+j], v[16c+j], q[16c+8+j] * v[16c+8+j])
-// A lane PAIR owns one row: lane h of the pair carries S_{4h..4h+3} and reads the 16-byte pieces
-// {16c+4h.., 16c+8+4h..} of every chunk, so the pair's two loads cover one 32-byte sector each and a warp
-// evaluates 16 rows per pass with up to 8 independent 128-bit loads in flight per lane.
+// then x_j = S_j + S_{j+4}, r = (x1+x3)+(x0+x2) (L2) resp. r = ((1-(S4+S5)) - ((S0+S1)+(S2+S3))) - (S6+S7) (IP), then a
+// scalar tail.  Rows are stored in HBM so that this order is also the coalesced order (graph.h row_pos): EIGHT lanes
+// own a row, lane t IS the AVX lane j = t, and the 16-byte piece t of every 128-byte block holds exactly the four
+// floats lane j needs from two consecutive chunks.  One warp-wide 128-bit load therefore reads four whole cache
+// lines (4 rows x 128 B) — a quarter of the L1TEX wavefronts of a sector-per-lane-pair layout — and the
+// accumulation needs no shuffles until the final horizontal step.  16 rows are in flight per warp
+// (4 row groups x 4 passes), i.e. 16 independent 128-bit loads per lane at d = 128.
 // ---------------------------------------------------------------------------------------------------------------
 
 template <bool IP>
-__device__ __forceinline__ void chunk_accumulate(const float4& qa, const float4& qb, const float4& a, const float4& b,
-                                                 float& s0, float& s1, float& s2, float& s3) {
+__device__ __forceinline__ void block_accumulate(const float4& q, const float4& a, float& s, bool second_chunk) {
   if (IP) {
-    s0 = __fadd_rn(s0, __fmaf_rn(qa.x, a.x, __fmul_rn(qb.x, b.x)));
-    s1 = __fadd_rn(s1, __fmaf_rn(qa.y, a.y, __fmul_rn(qb.y, b.y)));
-    s2 = __fadd_rn(s2, __fmaf_rn(qa.z, a.z, __fmul_rn(qb.z, b.z)));
-    s3 = __fadd_rn(s3, __fmaf_rn(qa.w, a.w, __fmul_rn(qb.w, b.w)));
+    s = __fadd_rn(s, __fmaf_rn(q.x, a.x, __fmul_rn(q.y, a.y)));
+    if (second_chunk) s = __fadd_rn(s, __fmaf_rn(q.z, a.z, __fmul_rn(q.w, a.w)));
   } else {
-    float d0, d1;
-    d0 = __fsub_rn(qa.x, a.x); d1 = __fsub_rn(qb.x, b.x); s0 = __fadd_rn(s0, __fmaf_rn(d0, d0, __fmul_rn(d1, d1)));
-    d0 = __fsub_rn(qa.y, a.y); d1 = __fsub_rn(qb.y, b.y); s1 = __fadd_rn(s1, __fmaf_rn(d0, d0, __fmul_rn(d1, d1)));
-    d0 = __fsub_rn(qa.z, a.z); d1 = __fsub_rn(qb.z, b.z); s2 = __fadd_rn(s2, __fmaf_rn(d0, d0, __fmul_rn(d1, d1)));
-    d0 = __fsub_rn(qa.w, a.w); d1 = __fsub_rn(qb.w, b.w); s3 = __fadd_rn(s3, __fmaf_rn(d0, d0, __fmul_rn(d1, d1)));
+    float d0 = __fsub_rn(q.x, a.x), d1 = __fsub_rn(q.y, a.y);
+    s = __fadd_rn(s, __fmaf_rn(d0, d0, __fmul_rn(d1, d1)));
+    if (second_chunk) {
+      d0 = __fsub_rn(q.z, a.z); d1 = __fsub_rn(q.w, a.w);
+      s = __fadd_rn(s, __fmaf_rn(d0, d0, __fmul_rn(d1, d1)));
+    }
   }
 }
 
-// Horizontal step + scalar tail (distance.hh:40,112-115 / :134-139), both lanes of the pair get the result.
+// Horizontal step (distance.hh:40 / :134-139); the result is valid in lane t == 0 of the row group.
 template <bool IP>
-__device__ __forceinline__ float finish_row(float s0, float s1, float s2, float s3, int h, const float* s_q,
-                                            const float* row, uint32_t dim) {
-  const uint32_t d16 = dim & ~15u;
-  float r;
+__device__ __forceinline__ float horizontal(float s) {
   if (IP) {
-    // r = ((1 - (S4+S5)) - ((S0+S1)+(S2+S3))) - (S6+S7);  tail: t += q*v; r -= t
-    const float t01 = __fadd_rn(s0, s1), t23 = __fadd_rn(s2, s3);
-    const float p01 = __shfl_xor_sync(kFull, t01, 1), p23 = __shfl_xor_sync(kFull, t23, 1);
-    const float A = h ? __fadd_rn(p01, p23) : __fadd_rn(t01, t23);
-    const float B = h ? t01 : p01;
-    const float C = h ? t23 : p23;
-    r = __fsub_rn(__fsub_rn(__fsub_rn(1.0f, B), A), C);
-    if (dim & 15u) {
-      float t = 0.f;
-      for (uint32_t e = d16; e < dim; ++e) t = __fadd_rn(t, __fmul_rn(s_q[e], __ldg(row + e)));
-      r = __fsub_rn(r, t);
-    }
+    const float p = __fadd_rn(s, __shfl_xor_sync(kFull, s, 1));        // t=0: S0+S1, 2: S2+S3, 4: S4+S5, 6: S6+S7
+    const float a = __fadd_rn(p, __shfl_xor_sync(kFull, p, 2));        // t=0: (S0+S1)+(S2+S3)
+    const float b = __shfl_xor_sync(kFull, p, 4);                      // t=0: S4+S5
+    const float c = __shfl_xor_sync(kFull, p, 6);                      // t=0: S6+S7
+    return __fsub_rn(__fsub_rn(__fsub_rn(1.0f, b), a), c);
   } else {
-    // x_j = S_j + S_{j+4};  r = (x1 + x3) + (x0 + x2);  tail: r += (q-v)^2
-    const float x0 = __fadd_rn(s0, __shfl_xor_sync(kFull, s0, 1));
-    const float x1 = __fadd_rn(s1, __shfl_xor_sync(kFull, s1, 1));
-    const float x2 = __fadd_rn(s2, __shfl_xor_sync(kFull, s2, 1));
-    const float x3 = __fadd_rn(s3, __shfl_xor_sync(kFull, s3, 1));
-    r = __fadd_rn(__fadd_rn(x1, x3), __fadd_rn(x0, x2));
-    for (uint32_t e = d16; e < dim; ++e) {
-      const float d = __fsub_rn(s_q[e], __ldg(row + e));
-      r = __fadd_rn(r, __fmul_rn(d, d));
-    }
+    const float x = __fadd_rn(s, __shfl_xor_sync(kFull, s, 4));        // t=j<4: x_j = S_j + S_{j+4}
+    const float y = __fadd_rn(x, __shfl_xor_sync(kFull, x, 2));        // t=0: x0+x2, t=1: x1+x3
+    return __fadd_rn(__shfl_xor_sync(kFull, y, 1), y);                 // t=0: (x1+x3)+(x0+x2)
   }
-  return r;
 }
 
-// dist(query, row) for rows s_rows[0..cnt) -> s_out[0..cnt).  s_q: the query in shared memory (16-byte aligned,
-// dim floats).  NCHUNK > 0: dim == 16*NCHUNK known at compile time (fully unrolled, all loads of a pass in flight);
-// NCHUNK == 0: any dim.
+// Scalar tail (distance.hh:112-115 / :134-139): the dim%16 trailing elements are added one by one, in order, to the
+// finished sum.  They follow the blocks in natural order (graph.h), lane t < 4 of the row group holds tail elements
+// 4t..4t+3 (loaded together with the first wave of blocks), and the running value is handed from lane to lane.
+template <bool IP>
+__device__ __forceinline__ float tail_chain(float r, const float4& q, const float4& v, uint32_t ntail, int t) {
+  float acc = IP ? 0.f : r;  // IP: t = sum q*v, then r -= t
+  for (int hop = 0; hop < 4; ++hop) {
+    if (4u * hop >= ntail) break;  // warp-uniform
+    if (hop > 0) acc = __shfl_up_sync(kFull, acc, 1);  // lane hop takes over from lane hop-1
+    if (t == hop) {
+      const float qs[4] = {q.x, q.y, q.z, q.w}, vs[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if (4u * hop + e < ntail) {
+          if (IP) acc = __fadd_rn(acc, __fmul_rn(qs[e], vs[e]));
+          else { const float d = __fsub_rn(qs[e], vs[e]); acc = __fadd_rn(acc, __fmul_rn(d, d)); }
+        }
+      }
+    }
+  }
+  // the finished value sits in lane (ntail-1)/4; bring it back to lane 0
+  const int last = static_cast<int>((ntail - 1) >> 2);
+  acc = __shfl_down_sync(kFull, acc, last);
+  return IP ? __fsub_rn(r, acc) : acc;
+}
+
 #ifdef SHN_EVAL_NOINLINE
 #define SHN_EVAL_ATTR __noinline__
 #else
 #define SHN_EVAL_ATTR __forceinline__
 #endif
-template <bool IP, int NCHUNK>
+// dist(query, row) for rows s_rows[0..cnt) -> s_out[0..cnt).  s_q: the query in shared memory in the stored layout
+// (16-byte aligned).  NCHUNK > 0: the dimension, fixed at compile time (96, 128, 200, 960: the shapes BASELINE.json
+// names); NCHUNK == 0: any dim.
+// PASSES: row groups of 4 evaluated together (4 = 16 rows in flight per warp, the beam-search setting; 1 = the compact
+// variant for the entry point, the greedy descent and the selection heuristic, where register pressure matters more).
+#ifndef SHN_PASSES
+#define SHN_PASSES 2
+#endif
+#ifndef SHN_SMALL_PASSES
+#define SHN_SMALL_PASSES 1
+#endif
+template <bool IP, int NCHUNK, int PASSES = SHN_PASSES>
 __device__ SHN_EVAL_ATTR void eval_rows(const DeviceGraph& g, const float* s_q, const uint32_t* s_rows, uint32_t cnt,
                                           float* s_out, int lane) {
-  const int h = lane & 1;
+  const int t = lane & 7, grp = lane >> 3;
   const float4* s_q4 = reinterpret_cast<const float4*>(s_q);
-  for (uint32_t base = 0; base < cnt; base += 16) {
-    const uint32_t i = base + (lane >> 1);
-    const uint32_t row = s_rows[i < cnt ? i : cnt - 1];  // clamp: a redundant load instead of a divergent branch
-    const float4* rp = g.vec + static_cast<size_t>(row) * g.row_f4;
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-    if (NCHUNK > 0) {
-      constexpr int NC = NCHUNK > 0 ? NCHUNK : 1;
-      constexpr int STEP = NC < SHN_STEP ? NC : SHN_STEP;  // chunks per wave of loads (2 loads each)
+  // NCHUNK > 0 is the dimension itself, known at compile time: block count, odd last chunk and tail length fold to
+  // constants and the wave loop unrolls completely
+  const uint32_t dim = NCHUNK > 0 ? static_cast<uint32_t>(NCHUNK) : g.dim;
+  const uint32_t nblk = row_blocks(dim);
+  const bool odd = (dim >> 4) & 1u;
+  const uint32_t ntail = dim & 15u;
+  constexpr int WAVE = 4;  // blocks per wave of loads: 4 rows x 4 blocks = 16 loads in flight per lane
+  for (uint32_t base = 0; base < cnt; base += 4 * PASSES) {
+    const float4* rp[PASSES];
+    float s[PASSES];
 #pragma unroll
-      for (int c0 = 0; c0 < NC; c0 += STEP) {
-        float4 a[STEP], b[STEP];
+    for (int p = 0; p < PASSES; ++p) {
+      s[p] = 0.f;
+      const uint32_t i = base + 4 * p + grp;
+      const uint32_t row = s_rows[i < cnt ? i : cnt - 1];  // clamp: a redundant load instead of a divergent branch
+      rp[p] = g.vec + static_cast<size_t>(row) * g.row_f4 + t;
+    }
+    const uint32_t npass = min(static_cast<uint32_t>(PASSES), (cnt - base + 3) >> 2);  // warp-uniform: passes that hold at least one row
+    float4 tv[PASSES];
+    if (ntail) {
 #pragma unroll
-        for (int c = 0; c < STEP; ++c) {
-          if (c0 + c < NC) {
-            a[c] = ldg_f4(rp + (c0 + c) * 4 + h);
-            b[c] = ldg_f4(rp + (c0 + c) * 4 + 2 + h);
+      for (int p = 0; p < PASSES; ++p) {
+        tv[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (static_cast<uint32_t>(p) < npass && 4u * t < ntail) tv[p] = ldg_f4(rp[p] + 8 * nblk);  // rp already includes + t
+      }
+    }
+    for (uint32_t b0 = 0; b0 < nblk; b0 += WAVE) {
+      float4 v[PASSES][WAVE];
+#pragma unroll
+      for (int p = 0; p < PASSES; ++p) {
+        if (static_cast<uint32_t>(p) < npass) {
+#pragma unroll
+          for (int w = 0; w < WAVE; ++w) {
+            if (b0 + w < nblk) v[p][w] = ldg_f4(rp[p] + 8 * (b0 + w));
           }
-        }
-#pragma unroll
-        for (int c = 0; c < STEP; ++c) {
-          if (c0 + c < NC) chunk_accumulate<IP>(s_q4[(c0 + c) * 4 + h], s_q4[(c0 + c) * 4 + 2 + h], a[c], b[c], s0, s1, s2, s3);
         }
       }
-    } else {
-      const uint32_t nchunk = g.dim >> 4;
-      for (uint32_t c0 = 0; c0 < nchunk; c0 += SHN_GSTEP) {
-        float4 a[SHN_GSTEP], b[SHN_GSTEP];
 #pragma unroll
-        for (int c = 0; c < SHN_GSTEP; ++c) {
-          if (c0 + c < nchunk) {
-            a[c] = ldg_f4(rp + (c0 + c) * 4 + h);
-            b[c] = ldg_f4(rp + (c0 + c) * 4 + 2 + h);
+      for (int w = 0; w < WAVE; ++w) {
+        if (b0 + w < nblk) {
+          const float4 q = s_q4[8 * (b0 + w) + t];
+          const bool second = !(odd && b0 + w == nblk - 1);
+#pragma unroll
+          for (int p = 0; p < PASSES; ++p) {
+            if (static_cast<uint32_t>(p) < npass) block_accumulate<IP>(q, v[p][w], s[p], second);
           }
-        }
-#pragma unroll
-        for (int c = 0; c < SHN_GSTEP; ++c) {
-          if (c0 + c < nchunk) chunk_accumulate<IP>(s_q4[(c0 + c) * 4 + h], s_q4[(c0 + c) * 4 + 2 + h], a[c], b[c], s0, s1, s2, s3);
         }
       }
     }
-    const float r = finish_row<IP>(s0, s1, s2, s3, h, s_q, reinterpret_cast<const float*>(rp), g.dim);
-    if (h == 0 && i < cnt) s_out[i] = r;
+#pragma unroll
+    for (int p = 0; p < PASSES; ++p) {
+      if (static_cast<uint32_t>(p) < npass) {
+        float r = horizontal<IP>(s[p]);
+        if (ntail) {
+          r = __shfl_sync(kFull, r, lane & ~7);  // every lane of the group starts from the group's sum
+          r = tail_chain<IP>(r, s_q4[8 * nblk + (t & 3)], tv[p], ntail, t);
+        }
+        const uint32_t i = base + 4 * p + grp;
+        if (t == 0 && i < cnt) s_out[i] = r;
+      }
+    }
   }
   __syncwarp();
 }
@@ -446,7 +483,7 @@ __device__ __forceinline__ bool greedy_step(const DeviceGraph& g, const float* s
   if (nb != kInvalid) s_rows[lane] = nb;
   __syncwarp();
   if (cnt == 0) return false;
-  eval_rows<IP, NCHUNK>(g, s_q, s_rows, cnt, s_dist, lane);
+  eval_rows<IP, NCHUNK, SHN_SMALL_PASSES>(g, s_q, s_rows, cnt, s_dist, lane);
   c_vis += cnt; c_dist += cnt;
   // sequential scan with strict '<' (hnsw.hh:378-382) == first index of the list minimum, if it beats closest
   float bd = static_cast<uint32_t>(lane) < cnt ? s_dist[lane] : __int_as_float(0x7f800000);
