@@ -142,31 +142,14 @@ def build_index(pkg, wl, base_dev, gpu):
     return ix, how, time.time() - t0
 
 
-def ground_truth(base_dev, q_dev, k, ip):
-    """Exact top-k for the recall check (plumbing, not timed): fp32 blocked matmul + re-rank in fp64 on the top 4k."""
+def ground_truth(pkg, base_dev, q_dev, k, ip, gpu):
+    """Exact top-k for the recall check: shn_bruteforce_topk_device (csrc/bruteforce.cu), outside every timed region."""
     nq = q_dev.shape[0]
-    out = torch.empty((nq, k), dtype=torch.int64, device=q_dev.device)
-    step = 2_000_000
-    bn = None if ip else (base_dev * base_dev).sum(1)
-    for qs in range(0, nq, 1024):
-        q = q_dev[qs:qs + 1024]
-        best_d = best_i = None
-        for s in range(0, base_dev.shape[0], step):
-            b = base_dev[s:s + step]
-            d = -(q @ b.T) if ip else bn[s:s + step][None, :] - 2.0 * (q @ b.T)
-            dd, ii = torch.topk(d, min(4 * k, d.shape[1]), dim=1, largest=False)
-            ii += s
-            best_d = dd if best_d is None else torch.cat([best_d, dd], 1)
-            best_i = ii if best_i is None else torch.cat([best_i, ii], 1)
-            if best_d.shape[1] > 8 * k:
-                dd, sel = torch.topk(best_d, 4 * k, dim=1, largest=False)
-                best_d, best_i = dd, torch.gather(best_i, 1, sel)
-        cand = base_dev[best_i.reshape(-1)].reshape(q.shape[0], -1, base_dev.shape[1]).double()
-        qq = q.double()[:, None, :]
-        ex = -(cand * qq).sum(2) if ip else ((cand - qq) ** 2).sum(2)
-        _, sel = torch.topk(ex, k, dim=1, largest=False)
-        out[qs:qs + 1024] = torch.gather(best_i, 1, sel)
-    return out
+    out = torch.empty((nq, k), dtype=torch.int32, device=q_dev.device)
+    torch.cuda.synchronize()
+    pkg.bruteforce_topk_device(base_dev.data_ptr(), base_dev.shape[0], q_dev.data_ptr(), nq, base_dev.shape[1], k,
+                               out.data_ptr(), ip=ip, gpu=gpu)
+    return out.long()
 
 
 def recall_at_k(ids_dev, gt_dev):
@@ -248,7 +231,9 @@ def main():
 
     # ---- ef selection: the smallest ef of the sweep with recall@10 >= 0.9 (rank 0 decides) -----------------------
     nrec = min(args.recall_queries, nq)
-    gt = ground_truth(base, batches[0][:nrec], K, wl["ip"])
+    t0 = time.time()
+    gt = ground_truth(pkg, base, batches[0][:nrec].contiguous(), K, wl["ip"], local_rank)
+    log(f"[rank {rank}] ground truth for {nrec} queries (brute force on the GPU): {time.time() - t0:.1f}s")
     sweep = []
     for ef in EF_SWEEP:
         st = ix.search_device(batches[0].data_ptr(), nq, K, ef, ids.data_ptr(), dists.data_ptr(), stream=stream)

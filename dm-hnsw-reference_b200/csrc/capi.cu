@@ -549,6 +549,48 @@ int shn_search(shn_index* ix, const float* queries, uint64_t nq, uint32_t k, uin
   return SHN_OK;
 }
 
+int shn_bruteforce_topk_device(const float* d_base, uint64_t n, const float* d_queries, uint64_t nq, uint32_t dim,
+                               shn_metric metric, uint32_t k, uint32_t* d_out_ids, float* d_out_dists, int gpu_id,
+                               void* stream) {
+  if (!d_base || !d_queries || !d_out_ids) return fail(SHN_ERR_ARG, "null buffer");
+  if (n == 0 || dim == 0 || k == 0 || k > 256) return fail(SHN_ERR_ARG, "need n >= 1, dim >= 1, 1 <= k <= 256");
+  if (n >= kInvalid || nq >= kInvalid) return fail(SHN_ERR_ARG, "n and nq must be below 2^32 - 1");
+  int sms = 0;
+  int rc = select_device(gpu_id, &sms);
+  if (rc != SHN_OK) return rc;
+  cudaError_t e = bruteforce_launch(d_base, n, d_queries, static_cast<uint32_t>(nq), dim, metric == SHN_IP, k, d_out_ids,
+                                    d_out_dists, sms, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return fail(SHN_ERR_CUDA, "bruteforce: %s", cudaGetErrorString(e));
+  return SHN_OK;
+}
+
+int shn_bruteforce_topk(const float* base, uint64_t n, const float* queries, uint64_t nq, uint32_t dim, shn_metric metric,
+                        uint32_t k, uint32_t* out_ids, float* out_dists, int gpu_id) {
+  if (!base || !queries || !out_ids) return fail(SHN_ERR_ARG, "null buffer");
+  int sms = 0;
+  int rc = select_device(gpu_id, &sms);
+  if (rc != SHN_OK) return rc;
+  if (nq == 0) return SHN_OK;
+  float *d_base = nullptr, *d_q = nullptr, *d_d = nullptr;
+  uint32_t* d_i = nullptr;
+  cudaError_t e = cudaMalloc(&d_base, n * dim * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&d_q, nq * dim * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&d_i, nq * k * sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaMalloc(&d_d, nq * k * sizeof(float));
+  if (e == cudaSuccess) e = cudaMemcpy(d_base, base, n * dim * sizeof(float), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(d_q, queries, nq * dim * sizeof(float), cudaMemcpyHostToDevice);
+  rc = SHN_OK;
+  if (e != cudaSuccess) rc = fail(SHN_ERR_CUDA, "staging: %s", cudaGetErrorString(e));
+  if (rc == SHN_OK) rc = shn_bruteforce_topk_device(d_base, n, d_q, nq, dim, metric, k, d_i, d_d, gpu_id, nullptr);
+  if (rc == SHN_OK) {
+    e = cudaMemcpy(out_ids, d_i, nq * k * sizeof(uint32_t), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && out_dists) e = cudaMemcpy(out_dists, d_d, nq * k * sizeof(float), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) rc = fail(SHN_ERR_CUDA, "copy back: %s", cudaGetErrorString(e));
+  }
+  cudaFree(d_base); cudaFree(d_q); cudaFree(d_i); cudaFree(d_d);
+  return rc;
+}
+
 const char* shn_last_error(void) { return g_err.c_str(); }
 const char* shn_version(void) { return "shn_b200 0.1 (sm_100a)"; }
 

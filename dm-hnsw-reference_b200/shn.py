@@ -67,6 +67,10 @@ def lib():
                                       C.c_uint32, C.c_int, C.c_uint32, C.c_int]
         L.shn_index_build_device.argtypes = L.shn_index_build.argtypes
         L.shn_index_build_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
+        L.shn_bruteforce_topk.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_uint32, C.c_int, C.c_uint32,
+                                          C.c_void_p, C.c_void_p, C.c_int]
+        L.shn_bruteforce_topk_device.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_uint32, C.c_int,
+                                                 C.c_uint32, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.shn_set_build_option.argtypes = [C.c_char_p, C.c_int64]
         L.shn_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int64]
         L.shn_search.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p,
@@ -220,3 +224,19 @@ def repartition_dumps(dumps, dim, m, n_parts_out):
 
 def set_build_option(key, value):
     _check(lib().shn_set_build_option(key.encode(), int(value)))
+
+
+def bruteforce_topk(base, queries, k, ip=False, gpu=0):
+    """Exact top-k on the GPU (host arrays in, host arrays out): ids [nq,k] u32 (row numbers), dists [nq,k] f32."""
+    b = np.ascontiguousarray(base, dtype=np.float32)
+    q = np.ascontiguousarray(queries, dtype=np.float32)
+    ids = np.empty((q.shape[0], k), np.uint32)
+    dists = np.empty((q.shape[0], k), np.float32)
+    _check(lib().shn_bruteforce_topk(b.ctypes.data, b.shape[0], q.ctypes.data, q.shape[0], b.shape[1], IP if ip else L2, k,
+                                     ids.ctypes.data, dists.ctypes.data, gpu))
+    return ids, dists
+
+
+def bruteforce_topk_device(d_base, n, d_queries, nq, dim, k, d_ids, d_dists=0, ip=False, gpu=0, stream=0):
+    _check(lib().shn_bruteforce_topk_device(d_base, n, d_queries, nq, dim, IP if ip else L2, k, d_ids, d_dists or None, gpu,
+                                            stream or None))

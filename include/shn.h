@@ -125,6 +125,18 @@ int shn_search(shn_index*, const float* queries, uint64_t nq, uint32_t k, uint32
 int shn_search_device(shn_index*, const float* d_queries, uint64_t nq, uint32_t k, uint32_t ef, uint32_t* d_out_ids,
                       float* d_out_dists, uint32_t* d_per_query_counters, void* stream, shn_stats* stats);
 
+/* ---- ground truth ------------------------------------------------------------------------------------------ */
+
+/* Exact top-k by brute force (the reference only reads ground truth produced offline, compute_node.cc:317,588).
+ * Host buffers; ids are row numbers of base; distances are fp32 squared L2 or 1 - dot accumulated with one fma per
+ * element in element order; ascending, ties broken by the lower id; k <= 256.  The *_device variant takes device
+ * pointers on gpu_id and synchronises the stream before it returns. */
+int shn_bruteforce_topk(const float* base, uint64_t n, const float* queries, uint64_t nq, uint32_t dim,
+                        shn_metric metric, uint32_t k, uint32_t* out_ids, float* out_dists, int gpu_id);
+int shn_bruteforce_topk_device(const float* d_base, uint64_t n, const float* d_queries, uint64_t nq, uint32_t dim,
+                               shn_metric metric, uint32_t k, uint32_t* d_out_ids, float* d_out_dists, int gpu_id,
+                               void* stream);
+
 const char* shn_last_error(void);
 const char* shn_version(void);
 

@@ -1,0 +1,43 @@
+"""shn_bruteforce_topk: exact ground truth on the GPU vs a float64 numpy reference."""
+import numpy as np
+import pytest
+
+import datagen
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("n,nq,dim,k,ip", [(5000, 70, 32, 10, False), (3001, 1, 128, 100, False), (2000, 65, 40, 7, True),
+                                           (129, 200, 8, 20, False), (50, 3, 200, 64, True), (100000, 300, 96, 10, False)])
+def test_matches_float64(pkg, n, nq, dim, k, ip):
+    base, queries = datagen.base_and_queries(n, nq, dim, normalize=ip)
+    ids, dists = pkg.bruteforce_topk(base, queries, k, ip=ip)
+    kk = min(k, n)
+    b, q = base.astype(np.float64), queries.astype(np.float64)
+    exact = 1.0 - q @ b.T if ip else ((q[:, None, :] - b[None, :, :]) ** 2).sum(2) if n * nq < 2e6 else \
+        (q * q).sum(1)[:, None] - 2 * q @ b.T + (b * b).sum(1)[None, :]
+    want = np.sort(exact, axis=1)[:, :kk]
+    assert (ids[:, :kk] < n).all() and (ids[:, kk:] == 0xFFFFFFFF).all()
+    got_exact = np.take_along_axis(exact, ids[:, :kk].astype(np.int64), 1)
+    assert np.allclose(got_exact, want, rtol=1e-5, atol=1e-5), "not the k nearest"
+    assert np.allclose(dists[:, :kk], want, rtol=1e-4, atol=1e-5)
+    assert (np.diff(dists[:, :kk], axis=1) >= 0).all()
+    for row in ids[:, :kk]:
+        assert len(set(row.tolist())) == kk
+
+
+def test_ties_break_by_lower_id(pkg):
+    base = np.zeros((300, 16), np.float32)
+    base[100:] = 1.0
+    ids, dists = pkg.bruteforce_topk(base, np.zeros((2, 16), np.float32), 10)
+    assert (ids == np.arange(10)).all() and (dists == 0).all()
+
+
+def test_recall_of_the_index_against_gpu_ground_truth(pkg):
+    n, dim = 20000, 64
+    base, queries = datagen.base_and_queries(n, 500, dim)
+    gt, _ = pkg.bruteforce_topk(base, queries, 10)
+    assert (gt == datagen.bruteforce(base, queries, 10)).mean() > 0.999
+    with pkg.Index.build(base, 16, 200) as ix:
+        ids, _, _ = ix.search(queries, 10, 64)
+    assert datagen.recall(ids, gt) > 0.98

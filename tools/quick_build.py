@@ -20,7 +20,7 @@ ix = pkg.Index.build_device(base.data_ptr(), n, dim, 16, efc, ip=ip)
 bs = ix.build_stats()
 print(f"build n={n} dim={dim} efc={efc}: {time.time() - t:.1f}s wall, {bs['kernel_ms'] / 1e3:.1f}s device, "
       f"{n / bs['kernel_ms'] * 1e3 / 1e3:.1f}k inserts/s, distcomps/insert {bs['distcomps'] / n:.0f}, max_level {ix.max_level}", flush=True)
-gt = bench.ground_truth(base, q[:5000], 10, ip)
+gt = bench.ground_truth(pkg, base, q[:5000].contiguous(), 10, ip, 0)
 ids = torch.empty((nq, 10), dtype=torch.int32, device=dev)
 dists = torch.empty((nq, 10), dtype=torch.float32, device=dev)
 for ef in efs:
