@@ -76,12 +76,23 @@ struct shn_index {
   int warps_per_sm = 0;
   uint32_t vis_cap = 0;
   shn_stats build_stats{};
+  // partitioned handle (shn_index_partition): d_vec / d_l0 / d_up_base hold the replicated hot set
+  uint32_t hot = 0, world = 1, rank = 0, own = 0, attached = 1;
+  float4* d_own_vec = nullptr;
+  uint32_t* d_own_l0 = nullptr;
+  const float4** d_part_vec = nullptr;   // device table [world]
+  const uint32_t** d_part_l0 = nullptr;
+  void* peer_vec[8] = {nullptr};         // what cudaIpcOpenMemHandle returned (to close)
+  void* peer_l0[8] = {nullptr};
+  uint32_t* d_visits = nullptr;          // [n] when visit counting is on
   bool built = false;
 
   DeviceGraph view() const {
     DeviceGraph g;
     g.vec = d_vec; g.l0 = d_l0; g.up_base = d_up_base; g.up = d_up; g.ext_id = d_ext_id;
     g.n = n; g.dim = dim; g.m = m; g.m0 = 2 * m; g.row_f4 = row_f4; g.ep_row = ep_row; g.ep_level = max_level_of_ep;
+    g.hot = world > 1 ? hot : n; g.world = world; g.rank = rank;
+    g.part_vec = d_part_vec; g.part_l0 = d_part_l0; g.visit_count = d_visits;
     return g;
   }
   uint32_t max_level_of_ep = 0;
@@ -144,6 +155,7 @@ int upload(shn_index* ix, const HostGraph& g) {
 }
 
 int download(const shn_index* ix, HostGraph& g) {
+  if (ix->world > 1) return fail(SHN_ERR_STATE, "a partitioned handle holds only its share of the index and cannot be stored");
   g = HostGraph{};
   g.n = ix->n; g.dim = ix->dim; g.m = ix->m; g.ep_row = ix->ep_row; g.max_level = ix->max_level; g.n_up = ix->n_up;
   const size_t row_floats = static_cast<size_t>(ix->row_f4) * 4, m0 = 2ull * ix->m;
@@ -242,6 +254,7 @@ void fill_stats(const shn_index* ix, const unsigned long long* t, uint64_t nq, s
   s->reference_layout_bytes = ref_node_bytes(ix->dim) * (t[kDistcomps] - nq) + ref_list0_bytes(ix->m) * t[kListsL0] +
                               ref_listu_bytes(ix->m) * t[kListsUpper];
   s->overflow_queries = t[kOverflowQueries];
+  s->rows_hot = t[kRowsHot]; s->rows_local = t[kRowsLocal]; s->rows_remote = t[kRowsRemote];
   s->processed = nq;
 }
 
@@ -264,6 +277,7 @@ int check_search_args(const shn_index* ix, uint64_t nq, uint32_t k, uint32_t ef)
   if (ef < k) return fail(SHN_ERR_ARG, "ef_search must be >= k (hnsw.hh:36): ef=%u k=%u", ef, k);
   if (ef > 4096) return fail(SHN_ERR_ARG, "ef_search %u exceeds the supported maximum 4096", ef);
   if (nq >= kInvalid) return fail(SHN_ERR_ARG, "too many queries in one call");
+  if (ix->world > 1 && ix->attached != ix->world) return fail(SHN_ERR_STATE, "partitioned handle: %u of %u partitions attached", ix->attached, ix->world);
   return SHN_OK;
 }
 
@@ -462,6 +476,11 @@ void shn_index_free(shn_index* ix) {
   if (ix->stream) cudaStreamSynchronize(ix->stream);
   cudaFree(ix->d_vec); cudaFree(ix->d_l0); cudaFree(ix->d_up_base); cudaFree(ix->d_up); cudaFree(ix->d_ext_id);
   cudaFree(ix->d_level);
+  for (int i = 0; i < 8; ++i) {
+    if (ix->peer_vec[i]) cudaIpcCloseMemHandle(ix->peer_vec[i]);
+    if (ix->peer_l0[i]) cudaIpcCloseMemHandle(ix->peer_l0[i]);
+  }
+  cudaFree(ix->d_own_vec); cudaFree(ix->d_own_l0); cudaFree(ix->d_part_vec); cudaFree(ix->d_part_l0); cudaFree(ix->d_visits);
   cudaFree(ix->ws.counter); cudaFree(ix->ws.totals);
   ix->ovf.release(); ix->q_stage.release(); ix->dist_stage.release(); ix->id_stage.release();
   for (auto& e : ix->ev) if (e) cudaEventDestroy(e);
@@ -546,6 +565,144 @@ int shn_search(shn_index* ix, const float* queries, uint64_t nq, uint32_t k, uin
     stats->kernel_ms = ker; stats->h2d_ms = h2d; stats->d2h_ms = d2h;
   }
   if (t[kFailedQueries]) return fail(SHN_ERR_CAPACITY, "%llu queries overflowed the visited set (ef=%u)", t[kFailedQueries], ef);
+  return SHN_OK;
+}
+
+int shn_index_count_visits(shn_index* ix, int enable) {
+  if (!ix) return fail(SHN_ERR_ARG, "null index handle");
+  if (ix->world > 1) return fail(SHN_ERR_STATE, "visit counting belongs to the full index, before it is partitioned");
+  CU(cudaSetDevice(ix->gpu));
+  CU(cudaStreamSynchronize(ix->stream));
+  if (!enable) { cudaFree(ix->d_visits); ix->d_visits = nullptr; return SHN_OK; }
+  if (!ix->d_visits) CU(cudaMalloc(&ix->d_visits, static_cast<size_t>(ix->n) * sizeof(uint32_t)));
+  CU(cudaMemset(ix->d_visits, 0, static_cast<size_t>(ix->n) * sizeof(uint32_t)));
+  return SHN_OK;
+}
+
+int shn_index_visit_counts(shn_index* ix, uint32_t* d_counts, int write_back) {
+  if (!ix || !d_counts) return fail(SHN_ERR_ARG, "null argument");
+  if (!ix->d_visits) return fail(SHN_ERR_STATE, "visit counting is off");
+  CU(cudaSetDevice(ix->gpu));
+  CU(cudaStreamSynchronize(ix->stream));
+  if (write_back) CU(cudaMemcpy(ix->d_visits, d_counts, static_cast<size_t>(ix->n) * sizeof(uint32_t), cudaMemcpyDeviceToDevice));
+  else CU(cudaMemcpy(d_counts, ix->d_visits, static_cast<size_t>(ix->n) * sizeof(uint32_t), cudaMemcpyDeviceToDevice));
+  return SHN_OK;
+}
+
+int shn_index_partition(shn_index** out, const shn_index* full, int rank, int world, uint32_t cache_ratio_pct) {
+  if (!out || !full) return fail(SHN_ERR_ARG, "null argument");
+  if (full->world > 1) return fail(SHN_ERR_STATE, "the handle is already a partition");
+  if (world < 2 || world > 8 || rank < 0 || rank >= world) return fail(SHN_ERR_ARG, "need 2 <= world <= 8 and 0 <= rank < world");
+  if (cache_ratio_pct > 100) return fail(SHN_ERR_ARG, "cache ratio is a percentage");
+  CU(cudaSetDevice(full->gpu));
+  CU(cudaStreamSynchronize(full->stream));
+  const uint32_t n = full->n;
+  // hot set: every node with level > 0, then the most visited level-0 nodes (ties: lower row) up to the cache budget
+  std::vector<uint32_t> level(n), visits;
+  CU(cudaMemcpy(level.data(), full->d_level, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  if (full->d_visits) {
+    visits.resize(n);
+    CU(cudaMemcpy(visits.data(), full->d_visits, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  }
+  std::vector<uint8_t> is_hot(n, 0);
+  uint64_t hot = 0;
+  for (uint32_t r = 0; r < n; ++r) if (level[r] > 0) { is_hot[r] = 1; ++hot; }
+  const uint64_t budget = std::min<uint64_t>(n, std::max<uint64_t>(hot, static_cast<uint64_t>(n) * cache_ratio_pct / 100));
+  if (hot < budget && !visits.empty()) {
+    std::vector<uint32_t> cand;
+    cand.reserve(n - hot);
+    for (uint32_t r = 0; r < n; ++r) if (!is_hot[r] && visits[r] > 0) cand.push_back(r);
+    const uint64_t want = std::min<uint64_t>(budget - hot, cand.size());
+    auto hotter = [&](uint32_t a, uint32_t b) { return visits[a] != visits[b] ? visits[a] > visits[b] : a < b; };
+    if (want < cand.size()) std::nth_element(cand.begin(), cand.begin() + want, cand.end(), hotter);
+    for (uint64_t i = 0; i < want; ++i) is_hot[cand[i]] = 1;
+    hot += want;
+  }
+  std::vector<uint32_t> new_of_old(n);
+  {
+    uint32_t next_hot = 0, next_cold = static_cast<uint32_t>(hot);
+    for (uint32_t r = 0; r < n; ++r) new_of_old[r] = is_hot[r] ? next_hot++ : next_cold++;
+  }
+  const uint32_t H = static_cast<uint32_t>(hot);
+  const uint32_t cold = n - H;
+  const uint32_t own = cold > static_cast<uint32_t>(rank) ? (cold - rank + world - 1) / world : 0;
+
+  shn_index* ix = nullptr;
+  int rc = new_handle(&ix, full->gpu, full->metric);
+  if (rc != SHN_OK) return rc;
+  auto bail = [&](int code) { shn_index_free(ix); return code; };
+#define CUB(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return bail(fail(SHN_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e__))); } while (0)
+  ix->n = n; ix->dim = full->dim; ix->m = full->m; ix->row_f4 = full->row_f4; ix->n_up = full->n_up; ix->max_level = full->max_level;
+  ix->max_level_of_ep = full->max_level_of_ep; ix->ep_row = new_of_old[full->ep_row];
+  ix->hot = H; ix->world = world; ix->rank = rank; ix->own = own; ix->attached = 1;
+  ix->warps_per_sm = full->warps_per_sm; ix->vis_cap = full->vis_cap; ix->dump_bytes = full->dump_bytes;
+  const size_t row_bytes = static_cast<size_t>(ix->row_f4) * 16, m0 = 2ull * ix->m;
+  uint32_t *d_new_of_old = nullptr, *d_old_of_new = nullptr;
+  CUB(cudaMalloc(&d_new_of_old, n * sizeof(uint32_t)));
+  CUB(cudaMalloc(&d_old_of_new, n * sizeof(uint32_t)));
+  CUB(cudaMemcpy(d_new_of_old, new_of_old.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  CUB(cudaMalloc(&ix->d_vec, std::max<size_t>(H, 1) * row_bytes));
+  CUB(cudaMalloc(&ix->d_l0, std::max<size_t>(H, 1) * m0 * sizeof(uint32_t)));
+  CUB(cudaMalloc(&ix->d_up_base, std::max<size_t>(H, 1) * sizeof(uint32_t)));
+  CUB(cudaMalloc(&ix->d_up, std::max<size_t>(ix->n_up, 1) * ix->m * sizeof(uint32_t)));
+  CUB(cudaMalloc(&ix->d_ext_id, n * sizeof(uint32_t)));
+  CUB(cudaMalloc(&ix->d_own_vec, std::max<size_t>(own, 1) * row_bytes));
+  CUB(cudaMalloc(&ix->d_own_l0, std::max<size_t>(own, 1) * m0 * sizeof(uint32_t)));
+  CUB(cudaMalloc(&ix->d_part_vec, 8 * sizeof(void*)));
+  CUB(cudaMalloc(&ix->d_part_l0, 8 * sizeof(void*)));
+  CUB(cudaMemset(ix->d_part_vec, 0, 8 * sizeof(void*)));
+  CUB(cudaMemset(ix->d_part_l0, 0, 8 * sizeof(void*)));
+  ix->hbm_bytes = H * (row_bytes + m0 * 4 + 4) + own * (row_bytes + m0 * 4) + n * 4ull + std::max<size_t>(ix->n_up, 1) * ix->m * 4;
+  PartitionJob job;
+  job.n = n; job.hot = H; job.own = own; job.rank = rank; job.world = world; job.row_f4 = ix->row_f4; job.m = ix->m; job.m0 = 2 * ix->m;
+  job.n_up = ix->n_up; job.new_of_old = d_new_of_old; job.old_of_new = d_old_of_new;
+  job.src_vec = full->d_vec; job.src_l0 = full->d_l0; job.src_up_base = full->d_up_base; job.src_up = full->d_up; job.src_ext_id = full->d_ext_id;
+  job.hot_vec = ix->d_vec; job.own_vec = ix->d_own_vec; job.hot_l0 = ix->d_l0; job.own_l0 = ix->d_own_l0;
+  job.hot_up_base = ix->d_up_base; job.up = ix->d_up; job.ext_id = ix->d_ext_id;
+  cudaError_t e = partition_arrays(job, ix->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ix->stream);
+  cudaFree(d_new_of_old); cudaFree(d_old_of_new);
+  if (e != cudaSuccess) return bail(fail(SHN_ERR_CUDA, "partition_arrays: %s", cudaGetErrorString(e)));
+  const void* vp = ix->d_own_vec;
+  const void* lp = ix->d_own_l0;
+  CUB(cudaMemcpy(ix->d_part_vec + rank, &vp, sizeof(void*), cudaMemcpyHostToDevice));
+  CUB(cudaMemcpy(ix->d_part_l0 + rank, &lp, sizeof(void*), cudaMemcpyHostToDevice));
+#undef CUB
+  *out = ix;
+  return SHN_OK;
+}
+
+int shn_index_partition_export(const shn_index* ix, void* handles, uint64_t* raw_ptrs) {
+  if (!ix || ix->world < 2) return fail(SHN_ERR_STATE, "not a partitioned handle");
+  CU(cudaSetDevice(ix->gpu));
+  if (handles) {
+    cudaIpcMemHandle_t h[2];
+    CU(cudaIpcGetMemHandle(&h[0], ix->d_own_vec));
+    CU(cudaIpcGetMemHandle(&h[1], ix->d_own_l0));
+    std::memcpy(handles, h, sizeof h);
+  }
+  if (raw_ptrs) { raw_ptrs[0] = reinterpret_cast<uint64_t>(ix->d_own_vec); raw_ptrs[1] = reinterpret_cast<uint64_t>(ix->d_own_l0); }
+  return SHN_OK;
+}
+
+int shn_index_partition_attach(shn_index* ix, int peer, const void* handles, const uint64_t* raw_ptrs) {
+  if (!ix || ix->world < 2) return fail(SHN_ERR_STATE, "not a partitioned handle");
+  if (peer < 0 || peer >= static_cast<int>(ix->world) || peer == static_cast<int>(ix->rank)) return fail(SHN_ERR_ARG, "bad peer rank %d", peer);
+  if (!handles && !raw_ptrs) return fail(SHN_ERR_ARG, "need IPC handles or raw pointers");
+  CU(cudaSetDevice(ix->gpu));
+  void *vp = nullptr, *lp = nullptr;
+  if (raw_ptrs) {  // same process (tests, single-process multi-GPU): the pointers are usable as they are
+    vp = reinterpret_cast<void*>(raw_ptrs[0]); lp = reinterpret_cast<void*>(raw_ptrs[1]);
+  } else {         // another process: map its allocations (NVLink peer access is enabled by the open)
+    cudaIpcMemHandle_t h[2];
+    std::memcpy(h, handles, sizeof h);
+    CU(cudaIpcOpenMemHandle(&vp, h[0], cudaIpcMemLazyEnablePeerAccess));
+    CU(cudaIpcOpenMemHandle(&lp, h[1], cudaIpcMemLazyEnablePeerAccess));
+    ix->peer_vec[peer] = vp; ix->peer_l0[peer] = lp;
+  }
+  CU(cudaMemcpy(ix->d_part_vec + peer, &vp, sizeof(void*), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(ix->d_part_l0 + peer, &lp, sizeof(void*), cudaMemcpyHostToDevice));
+  ++ix->attached;
   return SHN_OK;
 }
 

@@ -11,7 +11,8 @@
 namespace shn {
 
 // Indices into the device-side totals array (u64 each), summed over the queries of one launch.
-enum Total { kDistcomps = 0, kVisitedUpper, kVisitedL0, kListsL0, kListsUpper, kOverflowQueries, kFailedQueries, kNumTotals };
+enum Total { kDistcomps = 0, kVisitedUpper, kVisitedL0, kListsL0, kListsUpper, kOverflowQueries, kFailedQueries,
+             kRowsHot, kRowsLocal, kRowsRemote, kNumTotals };
 
 // Per-query counter record written when the caller asks for it (shn_search_device per_query_counters).
 constexpr int kPerQueryWords = 6;  // distcomps, visited_nodes, visited_nodes_l0, lists_l0, lists_upper, overflow
@@ -48,6 +49,19 @@ cudaError_t bruteforce_launch(const float* d_base, uint64_t n, const float* d_qu
 // ---- row layout (layout.cu): natural order [n][dim] <-> stored order [n][row_f4*4] (graph.h row_pos), both on device
 cudaError_t rows_to_layout(const float* d_src, float* d_dst, uint64_t n, uint32_t dim, uint32_t row_f4, cudaStream_t stream);
 cudaError_t rows_from_layout(const float* d_src, float* d_dst, uint64_t n, uint32_t dim, uint32_t row_f4, cudaStream_t stream);
+
+// ---- partitioning (partition.cu)
+struct PartitionJob {
+  uint32_t n = 0, hot = 0, own = 0, rank = 0, world = 1, row_f4 = 0, m = 0, m0 = 0;
+  uint64_t n_up = 0;
+  const uint32_t* new_of_old = nullptr;  // [n] device
+  uint32_t* old_of_new = nullptr;        // [n] device scratch
+  const float4* src_vec = nullptr;
+  const uint32_t *src_l0 = nullptr, *src_up_base = nullptr, *src_up = nullptr, *src_ext_id = nullptr;
+  float4 *hot_vec = nullptr, *own_vec = nullptr;
+  uint32_t *hot_l0 = nullptr, *own_l0 = nullptr, *hot_up_base = nullptr, *up = nullptr, *ext_id = nullptr;
+};
+cudaError_t partition_arrays(const PartitionJob& job, cudaStream_t stream);
 
 // ---- construction (build.cu) ------------------------------------------------------------------------------------
 struct BuildJob {

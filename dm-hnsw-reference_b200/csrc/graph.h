@@ -70,15 +70,39 @@ void dump_sizes(const HostGraph& g, int n_parts, uint64_t* sizes);
 void emit_dumps(const HostGraph& g, int n_parts, void* const* dumps);
 
 // Device view, passed to kernels by value.
+//
+// One GPU: every row is in vec / l0 (hot == n, world == 1).  Partitioned over `world` GPUs (partition.cu): rows are
+// renumbered so that the replicated hot set comes first — rows [0, hot) (all nodes with level > 0 plus the most visited
+// level-0 nodes) live in every GPU's vec / l0, the HBM-resident stand-in for the reference's compute-node cache
+// (src/cache/cache.hh) — and row r >= hot lives on GPU (r - hot) % world at local index (r - hot) / world, as the
+// reference scatters nodes over memory nodes (src/compute_thread.hh:57); part_vec / part_l0 are device tables of the
+// `world` base pointers (peer-mapped for the other GPUs: what was an RDMA READ is a load over NVLink).
 struct DeviceGraph {
   const float4* vec;
   const uint32_t* l0;
-  const uint32_t* up_base;
+  const uint32_t* up_base;   // rows < hot only (every node with level > 0 is hot)
   const uint32_t* up;
   const uint32_t* ext_id;
   uint32_t n, dim, m, m0;
   uint32_t row_f4;    // row stride of vec in float4
   uint32_t ep_row, ep_level;
+  uint32_t hot, world, rank;
+  const float4* const* part_vec;
+  const uint32_t* const* part_l0;
+  uint32_t* visit_count;  // optional [n]: +1 per level-0 distance computation (warm-up pass that picks the hot set)
 };
+
+#ifdef __CUDACC__
+__device__ __forceinline__ const float4* vec_row(const DeviceGraph& g, uint32_t row) {
+  if (row < g.hot) return g.vec + static_cast<size_t>(row) * g.row_f4;
+  const uint32_t o = row - g.hot;
+  return g.part_vec[o % g.world] + static_cast<size_t>(o / g.world) * g.row_f4;
+}
+__device__ __forceinline__ const uint32_t* l0_row(const DeviceGraph& g, uint32_t row) {
+  if (row < g.hot) return g.l0 + static_cast<size_t>(row) * g.m0;
+  const uint32_t o = row - g.hot;
+  return g.part_l0[o % g.world] + static_cast<size_t>(o / g.world) * g.m0;
+}
+#endif
 
 }  // namespace shn

@@ -1,0 +1,74 @@
+// partition.cu — split a full index (one GPU) into the share one GPU of `world` keeps (graph.h DeviceGraph):
+// rows are renumbered hot-set first; the hot rows are replicated, the others dealt round-robin to the GPUs.
+#include "engine.h"
+
+namespace shn {
+namespace {
+
+__global__ void invert_perm_kernel(const uint32_t* __restrict__ new_of_old, uint32_t* __restrict__ old_of_new, uint32_t n) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) old_of_new[new_of_old[i]] = i;
+}
+
+// dst[i] = src[old_of_new[first + i * step]], rows of row_f4 float4; a warp per destination row
+__global__ void gather_rows_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ old_of_new, uint32_t first,
+                                   uint32_t step, uint32_t count, uint32_t row_f4, float4* __restrict__ dst) {
+  const uint32_t warps = gridDim.x * (blockDim.x >> 5);
+  const int lane = threadIdx.x & 31;
+  for (uint32_t i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < count; i += warps) {
+    const uint32_t old = old_of_new[first + static_cast<uint64_t>(i) * step];
+    for (uint32_t f = lane; f < row_f4; f += 32) dst[static_cast<size_t>(i) * row_f4 + f] = src[static_cast<size_t>(old) * row_f4 + f];
+  }
+}
+
+// dst[i][s] = remap(src[old_of_new[first + i*step]][s]); 0xFFFFFFFF stays
+__global__ void gather_lists_kernel(const uint32_t* __restrict__ src, uint32_t width, const uint32_t* __restrict__ old_of_new,
+                                    const uint32_t* __restrict__ new_of_old, uint32_t first, uint32_t step, uint32_t count,
+                                    uint32_t* __restrict__ dst) {
+  const uint64_t total = static_cast<uint64_t>(count) * width;
+  for (uint64_t t = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; t < total;
+       t += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+    const uint32_t i = static_cast<uint32_t>(t / width), s = static_cast<uint32_t>(t % width);
+    const uint32_t old = old_of_new[first + static_cast<uint64_t>(i) * step];
+    const uint32_t nb = src[static_cast<size_t>(old) * width + s];
+    dst[t] = nb == kInvalid ? kInvalid : new_of_old[nb];
+  }
+}
+
+__global__ void remap_kernel(const uint32_t* __restrict__ src, const uint32_t* __restrict__ new_of_old, uint64_t total,
+                             uint32_t* __restrict__ dst) {
+  for (uint64_t t = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; t < total;
+       t += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+    const uint32_t nb = src[t];
+    dst[t] = nb == kInvalid ? kInvalid : new_of_old[nb];
+  }
+}
+
+__global__ void gather_u32_kernel(const uint32_t* __restrict__ src, const uint32_t* __restrict__ old_of_new, uint32_t count,
+                                  uint32_t* __restrict__ dst) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) dst[i] = src[old_of_new[i]];
+}
+
+inline int grid_for(uint64_t work, int threads) {
+  return static_cast<int>(std::max<uint64_t>(1, std::min<uint64_t>((work + threads - 1) / threads, 148ull * 16)));
+}
+
+}  // namespace
+
+cudaError_t partition_arrays(const PartitionJob& j, cudaStream_t s) {
+  const uint32_t n = j.n, hot = j.hot;
+  invert_perm_kernel<<<grid_for(n, 256), 256, 0, s>>>(j.new_of_old, j.old_of_new, n);
+  // replicated hot set
+  gather_rows_kernel<<<grid_for(static_cast<uint64_t>(hot) * 32, 256), 256, 0, s>>>(j.src_vec, j.old_of_new, 0, 1, hot, j.row_f4, j.hot_vec);
+  gather_lists_kernel<<<grid_for(static_cast<uint64_t>(hot) * j.m0, 256), 256, 0, s>>>(j.src_l0, j.m0, j.old_of_new, j.new_of_old, 0, 1, hot, j.hot_l0);
+  gather_u32_kernel<<<grid_for(hot, 256), 256, 0, s>>>(j.src_up_base, j.old_of_new, hot, j.hot_up_base);
+  if (j.n_up) remap_kernel<<<grid_for(j.n_up * j.m, 256), 256, 0, s>>>(j.src_up, j.new_of_old, j.n_up * j.m, j.up);
+  gather_u32_kernel<<<grid_for(n, 256), 256, 0, s>>>(j.src_ext_id, j.old_of_new, n, j.ext_id);
+  // this GPU's share of the remaining rows: new ids hot + rank, hot + rank + world, ...
+  if (j.own) {
+    gather_rows_kernel<<<grid_for(static_cast<uint64_t>(j.own) * 32, 256), 256, 0, s>>>(j.src_vec, j.old_of_new, hot + j.rank, j.world, j.own, j.row_f4, j.own_vec);
+    gather_lists_kernel<<<grid_for(static_cast<uint64_t>(j.own) * j.m0, 256), 256, 0, s>>>(j.src_l0, j.m0, j.old_of_new, j.new_of_old, hot + j.rank, j.world, j.own, j.own_l0);
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace shn

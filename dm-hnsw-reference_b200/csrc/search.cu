@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, SHN_MIN_BLOCKS) search_ke
   vis.ovf_cap = p.ovf_cap; vis.ovf_limit = p.ovf_limit;
   vis.count = 0; vis.ovf_count = 0; vis.failed = false;
 
-  unsigned long long t_dist = 0, t_vup = 0, t_vl0 = 0, t_l0 = 0, t_lup = 0, t_ovf = 0, t_fail = 0;
+  unsigned long long t_dist = 0, t_vup = 0, t_vl0 = 0, t_l0 = 0, t_lup = 0, t_ovf = 0, t_fail = 0, t_hot = 0, t_local = 0, t_remote = 0;
   const uint32_t ef = p.ef;
 
   for (;;) {
@@ -98,7 +98,10 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, SHN_MIN_BLOCKS) search_ke
     visited_test_and_set(vis, cur, lane == 0, lane);
 
     // search_level<without_lock>(ef, level 0) (hnsw.hh:407-476)
-    beam_search<IP, NCHUNK>(g, s_q, 0, ef, qd, qi, qsize, s_rows, s_dist, vis, c_dist, c_vl0, c_l0, lane);
+    uint32_t c_hot = 0, c_local = 0;
+    const uint32_t l0_before = c_vl0;
+    beam_search<IP, NCHUNK>(g, s_q, 0, ef, qd, qi, qsize, s_rows, s_dist, vis, c_dist, c_vl0, c_l0, c_hot, c_local, lane);
+    if (g.world > 1) { t_hot += c_hot; t_local += c_local; t_remote += (c_vl0 - l0_before) - c_hot - c_local; }
 
     // trim to k (:296-298); the reference reports ids in heap-array order, here ascending by distance
     for (uint32_t j = lane; j < p.k; j += 32) {
@@ -125,6 +128,9 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, SHN_MIN_BLOCKS) search_ke
     atomicAdd(p.totals + kListsUpper, t_lup);
     if (t_ovf) atomicAdd(p.totals + kOverflowQueries, t_ovf);
     if (t_fail) atomicAdd(p.totals + kFailedQueries, t_fail);
+    if (t_hot) atomicAdd(p.totals + kRowsHot, t_hot);
+    if (t_local) atomicAdd(p.totals + kRowsLocal, t_local);
+    if (t_remote) atomicAdd(p.totals + kRowsRemote, t_remote);
   }
 }
 

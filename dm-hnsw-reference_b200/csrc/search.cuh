@@ -133,7 +133,7 @@ __device__ SHN_EVAL_ATTR void eval_rows(const DeviceGraph& g, const float* s_q, 
       s[p] = 0.f;
       const uint32_t i = base + 4 * p + grp;
       const uint32_t row = s_rows[i < cnt ? i : cnt - 1];  // clamp: a redundant load instead of a divergent branch
-      rp[p] = g.vec + static_cast<size_t>(row) * g.row_f4 + t;
+      rp[p] = vec_row(g, row) + t;
     }
     const uint32_t npass = min(static_cast<uint32_t>(PASSES), (cnt - base + 3) >> 2);  // warp-uniform: passes that hold at least one row
     float4 tv[PASSES];
@@ -391,7 +391,8 @@ __device__ __forceinline__ bool visited_test_and_set(VisitedSet& v, uint32_t id,
 template <bool IP, int NCHUNK>
 __device__ __forceinline__ void beam_search(const DeviceGraph& g, const float* s_q, uint32_t level, uint32_t ef, float* qd,
                                             uint32_t* qi, uint32_t& qsize, uint32_t* s_rows, float* s_dist, VisitedSet& vis,
-                                            uint32_t& c_dist, uint32_t& c_vis, uint32_t& c_lists, int lane) {
+                                            uint32_t& c_dist, uint32_t& c_vis, uint32_t& c_lists, uint32_t& c_hot,
+                                            uint32_t& c_local, int lane) {
   const uint32_t width = level == 0 ? g.m0 : g.m;
   uint32_t lb = 0;  // every entry below lb is expanded
   // The list of the entry most likely to be expanded NEXT (the closest unexpanded one after the current candidate)
@@ -420,7 +421,7 @@ __device__ __forceinline__ void beam_search(const DeviceGraph& g, const float* s
     if (cand == pre_row) {
       nb0 = pre0; nb1 = pre1;
     } else {
-      const uint32_t* list = level == 0 ? g.l0 + static_cast<size_t>(cand) * g.m0
+      const uint32_t* list = level == 0 ? l0_row(g, cand)
                                         : g.up + (static_cast<size_t>(__ldg(g.up_base + cand)) + (level - 1)) * g.m;
       nb0 = static_cast<uint32_t>(lane) < width ? __ldg(list + lane) : kInvalid;
       if (width > 32) nb1 = static_cast<uint32_t>(lane) + 32 < width ? __ldg(list + lane + 32) : kInvalid;
@@ -437,7 +438,7 @@ __device__ __forceinline__ void beam_search(const DeviceGraph& g, const float* s
       pre_row = kInvalid;
       if (pos2 != kInvalid) {
         pre_row = qi[pos2];
-        const uint32_t* list = level == 0 ? g.l0 + static_cast<size_t>(pre_row) * g.m0
+        const uint32_t* list = level == 0 ? l0_row(g, pre_row)
                                           : g.up + (static_cast<size_t>(__ldg(g.up_base + pre_row)) + (level - 1)) * g.m;
         pre0 = static_cast<uint32_t>(lane) < width ? __ldg(list + lane) : kInvalid;
         if (width > 32) pre1 = static_cast<uint32_t>(lane) + 32 < width ? __ldg(list + lane + 32) : kInvalid;
@@ -462,6 +463,17 @@ __device__ __forceinline__ void beam_search(const DeviceGraph& g, const float* s
     __syncwarp();
     if (cnt == 0) continue;
     c_vis += cnt; c_dist += cnt;
+    if (level == 0 && (g.world > 1 || g.visit_count)) {  // warp-uniform; never taken on the plain single-GPU path
+      for (uint32_t i = lane; i < ((cnt + 31u) & ~31u); i += 32) {
+        const uint32_t row = i < cnt ? s_rows[i] : 0u;
+        const bool in = i < cnt;
+        if (in && g.visit_count) atomicAdd(g.visit_count + row, 1u);
+        const bool hot = in && row < g.hot;
+        const bool mine = in && !hot && (row - g.hot) % g.world == g.rank;
+        c_hot += __popc(__ballot_sync(kFull, hot));
+        c_local += __popc(__ballot_sync(kFull, mine));
+      }
+    }
     eval_rows<IP, NCHUNK>(g, s_q, s_rows, cnt, s_dist, lane);
 
     // admission against the running farthest distance (:456-465, heap.hh:34-41), all neighbours in one merge

@@ -23,7 +23,8 @@ class Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("distcomps", "visited_nodes", "visited_nodes_l0", "visited_neighborlists",
                                           "lists_l0", "lists_upper", "algorithmic_bytes", "reference_layout_bytes",
                                           "overflow_queries", "processed")] + \
-               [("kernel_ms", C.c_double), ("h2d_ms", C.c_double), ("d2h_ms", C.c_double)]
+               [("kernel_ms", C.c_double), ("h2d_ms", C.c_double), ("d2h_ms", C.c_double)] + \
+               [(n, C.c_uint64) for n in ("rows_hot", "rows_local", "rows_remote")]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -71,6 +72,11 @@ def lib():
                                           C.c_void_p, C.c_void_p, C.c_int]
         L.shn_bruteforce_topk_device.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_uint32, C.c_int,
                                                  C.c_uint32, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.shn_index_count_visits.argtypes = [C.c_void_p, C.c_int]
+        L.shn_index_visit_counts.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.shn_index_partition.argtypes = [C.POINTER(C.c_void_p), C.c_void_p, C.c_int, C.c_int, C.c_uint32]
+        L.shn_index_partition_export.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]
+        L.shn_index_partition_attach.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_uint64)]
         L.shn_set_build_option.argtypes = [C.c_char_p, C.c_int64]
         L.shn_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int64]
         L.shn_search.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p,
@@ -128,6 +134,30 @@ class Index:
         h = C.c_void_p()
         _check(lib().shn_index_build_device(C.byref(h), d_base, d_ids or None, n, dim, m, efc, IP if ip else L2, seed, gpu))
         return cls(h, IP if ip else L2)
+
+    # -- multi-GPU partitioning -----------------------------------------------------------------------------------
+    def count_visits(self, enable=True):
+        _check(lib().shn_index_count_visits(self._h, int(enable)))
+
+    def visit_counts(self, d_counts, write_back=False):
+        """Copy the per-node visit counters to / from a device buffer of n u32 (raw pointer)."""
+        _check(lib().shn_index_visit_counts(self._h, d_counts, int(write_back)))
+
+    def partition(self, rank, world, cache_ratio_pct=5):
+        h = C.c_void_p()
+        _check(lib().shn_index_partition(C.byref(h), self._h, rank, world, cache_ratio_pct))
+        return Index(h, self.metric)
+
+    def partition_export(self):
+        """(128-byte IPC handle blob, (vec_ptr, l0_ptr))"""
+        buf = C.create_string_buffer(128)
+        raw = (C.c_uint64 * 2)()
+        _check(lib().shn_index_partition_export(self._h, buf, raw))
+        return buf.raw, (int(raw[0]), int(raw[1]))
+
+    def partition_attach(self, peer, handles=None, raw_ptrs=None):
+        raw = (C.c_uint64 * 2)(*raw_ptrs) if raw_ptrs is not None else None
+        _check(lib().shn_index_partition_attach(self._h, peer, handles, raw))
 
     def build_stats(self):
         st = Stats()

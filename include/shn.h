@@ -49,6 +49,11 @@ typedef struct {
   uint64_t processed;             /* statistics.hh processed */
   double kernel_ms;               /* CUDA-event time of the device work of this call */
   double h2d_ms, d2h_ms;          /* host<->device copies of this call (0 for the *_device entry points) */
+  /* partitioned handles only: where the level-0 rows of this call were read from (cache.hits_total = rows_hot +
+   * rows_local, cache.misses_total = rows_remote in the reference's JSON) */
+  uint64_t rows_hot;              /* replicated hot set in local HBM (the compute-node cache of src/cache/cache.hh) */
+  uint64_t rows_local;            /* this GPU's own partition */
+  uint64_t rows_remote;           /* a peer's partition, over NVLink (what the reference READs over RDMA) */
 } shn_stats;
 
 /* ---- index lifetime -------------------------------------------------------------------------------------- */
@@ -107,6 +112,23 @@ uint64_t shn_index_dump_bytes(const shn_index*); /* "index_size": bytes the refe
  * reference's own order (src/hnsw/distance.hh as compiled, see oracle/hnsw_oracle.c), so results are bit-identical
  * to the reference's except on exact distance ties. */
 int shn_set_option(shn_index*, const char* key, int64_t value);
+
+/* ---- multi-GPU: one global graph partitioned over the GPUs of a node ---------------------------------------------
+ * The reference scatters nodes over memory nodes (RemotePtr = memory node + offset, src/remote_pointer.hh:7-22,
+ * src/compute_thread.hh:57) and every hop is an RDMA READ (src/rdma/rdma_reads.hh) unless the compute-node cache holds
+ * the node (src/cache/cache.hh, admission src/hnsw/hnsw.hh:447-448).  Here: one process per GPU; each builds or loads the
+ * full index, (optionally) runs warm-up queries with visit counting, all-reduces the counts, and keeps
+ *   - the hot set (all nodes with level > 0 + the most visited level-0 nodes, cache_ratio_pct % of the nodes) replicated,
+ *   - 1/world of the remaining rows (round-robin);
+ * the other shares are read over NVLink through peer-mapped pointers.  Results do not depend on the partitioning. */
+int shn_index_count_visits(shn_index*, int enable);   /* on: allocate + zero the per-node counters; searches then count */
+/* copy the counters to (write_back = 0) or from (write_back = 1) a device buffer of n u32 — the caller all-reduces */
+int shn_index_visit_counts(shn_index*, uint32_t* d_counts, int write_back);
+int shn_index_partition(shn_index** out, const shn_index* full, int rank, int world, uint32_t cache_ratio_pct);
+/* handles: 128 bytes out (two cudaIpcMemHandle_t: vectors, level-0 lists) to send to the peers; raw_ptrs: 2 x u64 */
+int shn_index_partition_export(const shn_index*, void* handles, uint64_t* raw_ptrs);
+/* handles from rank `peer` (another process), or its raw pointers (same process).  Search needs every peer attached. */
+int shn_index_partition_attach(shn_index*, int peer, const void* handles, const uint64_t* raw_ptrs);
 
 /* ---- search ------------------------------------------------------------------------------------------------ */
 
