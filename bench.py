@@ -189,6 +189,10 @@ def main():
     ap.add_argument("--recall-queries", type=int, default=10_000)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--ef", type=int, default=0, help="fix ef instead of picking the smallest with recall >= 0.9")
+    ap.add_argument("--index-mode", default="replica", choices=["replica", "partitioned"],
+                    help="N > 1: every GPU holds the whole index (default) or 1/N of it plus a replicated hot set, "
+                         "the rest read over NVLink (SURVEY 8e)")
+    ap.add_argument("--cache-ratio", type=int, default=5, help="partitioned: hot set in %% of the nodes (--cache-ratio of the reference)")
     args = ap.parse_args()
     if args.warmup < 3:
         log("bench: raising --warmup to 3 (timing rules)")
@@ -215,6 +219,29 @@ def main():
     base = synth_rows(wl["n"], wl["dim"], 1001, dev, wl["normalize"])
     ix, how, build_s = build_index(pkg, wl, base, local_rank)
     log(f"[rank {rank}] index: {how}, {build_s:.1f}s, n={ix.n} max_level={ix.max_level} hbm={ix.hbm_bytes / 1e9:.2f} GB")
+
+    partitioned = dist is not None and args.index_mode == "partitioned"
+    if partitioned:
+        # warm-up pass with visit counting -> the same hot set on every rank -> keep 1/world of the cold rows and map
+        # the peers' shares (CUDA IPC handles travel over torch.distributed, the loads then go over NVLink)
+        t0 = time.time()
+        warm = synth_rows(min(nq, 200_000), wl["dim"], 7007 + rank, dev, wl["normalize"])
+        tmp_i = torch.empty((warm.shape[0], K), dtype=torch.int32, device=dev)
+        ix.count_visits(True)
+        ix.search_device(warm.data_ptr(), warm.shape[0], K, 64, tmp_i.data_ptr())
+        counts = torch.empty(ix.n, dtype=torch.int32, device=dev)
+        ix.visit_counts(counts.data_ptr())
+        dist.all_reduce(counts)
+        ix.visit_counts(counts.data_ptr(), write_back=True)
+        torch.cuda.synchronize()
+        part = ix.partition(rank, world, args.cache_ratio)
+        ix.close()
+        del counts, warm, tmp_i
+        par_mod = pkg.parallel
+        par_mod.exchange_partition_shares(part, rank, world, dist, os.environ.get("MASTER_PORT", "0"))
+        ix = part
+        how += f"; partitioned x{world}, hot set {args.cache_ratio}% replicated, peers' shares mapped through CUDA VMM file descriptors ({time.time() - t0:.1f}s)"
+        log(f"[rank {rank}] {how}; hbm={ix.hbm_bytes / 1e9:.2f} GB")
 
     # query batches: held-out draws of the same model; each rank its own shard (seed), 4 distinct batches rotate
     n_batches = 4
@@ -314,6 +341,12 @@ def main():
         kern_ms.append(st["kernel_ms"]); alg_bytes += st["algorithmic_bytes"]
     kern_avg_ms = float(np.mean(kern_ms))
     achieved = alg_bytes / args.steps / (kern_avg_ms * 1e-3) / 1e9
+    placement = None
+    if partitioned:
+        tot = max(1, st["rows_hot"] + st["rows_local"] + st["rows_remote"])
+        remote_bytes = st["rows_remote"] * (4 * wl["dim"]) + (st["rows_remote"] / tot) * st["lists_l0"] * 8 * wl["m"]
+        placement = dict(rows_hot=st["rows_hot"] / tot, rows_local=st["rows_local"] / tot, rows_remote=st["rows_remote"] / tot,
+                         nvlink_in_gbs=round(remote_bytes / (kern_ms[-1] * 1e-3) / 1e9, 1), nvlink_peak_gbs=770.0)
 
     # ---- end to end through the host-buffer C-ABI call (e2e) -------------------------------------------------------
     host_q = [torch.empty((nq, wl["dim"]), dtype=torch.float32).pin_memory() for _ in range(2)]
@@ -358,7 +391,8 @@ def main():
                 config=dict(workload=wl["label"], ef=ef, k=K, recall_at_10=recall, queries_per_step_per_gpu=nq,
                             index=how, index_build_s=round(build_s, 1), l2_policy="index (>= 6 GB at 10M rows) and the "
                             "rotating query batches are larger than the 126 MB L2; no flush",
-                            parallelism=f"replica x{world}, queries sharded, NCCL all-gather of top-k" if world > 1 else "single GPU"),
+                            parallelism=(f"{args.index_mode} x{world}, queries sharded, NCCL all-gather of top-k" if world > 1 else "single GPU"),
+                            placement=placement),
                 roofline=dict(bound="hbm", achieved=round(achieved, 1), peak=peak, unit="GB/s", frac=round(achieved / peak, 4),
                               traffic=(traffic or {}).get("dram_bytes_per_launch"), peak_source=peak_src,
                               kernel="search_kernel", kernel_ms=round(kern_avg_ms, 3),

@@ -8,6 +8,7 @@
 
 #include "../../include/shn.h"
 #include "engine.h"
+#include "vmm.h"
 
 using namespace shn;
 
@@ -82,8 +83,8 @@ struct shn_index {
   uint32_t* d_own_l0 = nullptr;
   const float4** d_part_vec = nullptr;   // device table [world]
   const uint32_t** d_part_l0 = nullptr;
-  void* peer_vec[8] = {nullptr};         // what cudaIpcOpenMemHandle returned (to close)
-  void* peer_l0[8] = {nullptr};
+  VmmBlock own_vec_blk, own_l0_blk;      // this GPU's share (exportable as POSIX fds)
+  VmmBlock peer_vec_blk[8], peer_l0_blk[8];  // shares of other processes mapped here
   uint32_t* d_visits = nullptr;          // [n] when visit counting is on
   bool built = false;
 
@@ -476,11 +477,9 @@ void shn_index_free(shn_index* ix) {
   if (ix->stream) cudaStreamSynchronize(ix->stream);
   cudaFree(ix->d_vec); cudaFree(ix->d_l0); cudaFree(ix->d_up_base); cudaFree(ix->d_up); cudaFree(ix->d_ext_id);
   cudaFree(ix->d_level);
-  for (int i = 0; i < 8; ++i) {
-    if (ix->peer_vec[i]) cudaIpcCloseMemHandle(ix->peer_vec[i]);
-    if (ix->peer_l0[i]) cudaIpcCloseMemHandle(ix->peer_l0[i]);
-  }
-  cudaFree(ix->d_own_vec); cudaFree(ix->d_own_l0); cudaFree(ix->d_part_vec); cudaFree(ix->d_part_l0); cudaFree(ix->d_visits);
+  for (int i = 0; i < 8; ++i) { vmm_free(ix->peer_vec_blk[i]); vmm_free(ix->peer_l0_blk[i]); }
+  vmm_free(ix->own_vec_blk); vmm_free(ix->own_l0_blk);
+  cudaFree(ix->d_part_vec); cudaFree(ix->d_part_l0); cudaFree(ix->d_visits);
   cudaFree(ix->ws.counter); cudaFree(ix->ws.totals);
   ix->ovf.release(); ix->q_stage.release(); ix->dist_stage.release(); ix->id_stage.release();
   for (auto& e : ix->ev) if (e) cudaEventDestroy(e);
@@ -646,8 +645,14 @@ int shn_index_partition(shn_index** out, const shn_index* full, int rank, int wo
   CUB(cudaMalloc(&ix->d_up_base, std::max<size_t>(H, 1) * sizeof(uint32_t)));
   CUB(cudaMalloc(&ix->d_up, std::max<size_t>(ix->n_up, 1) * ix->m * sizeof(uint32_t)));
   CUB(cudaMalloc(&ix->d_ext_id, n * sizeof(uint32_t)));
-  CUB(cudaMalloc(&ix->d_own_vec, std::max<size_t>(own, 1) * row_bytes));
-  CUB(cudaMalloc(&ix->d_own_l0, std::max<size_t>(own, 1) * m0 * sizeof(uint32_t)));
+  {
+    const char* why = "";
+    if (vmm_alloc(ix->own_vec_blk, std::max<size_t>(own, 1) * row_bytes, ix->gpu, &why) != cudaSuccess ||
+        vmm_alloc(ix->own_l0_blk, std::max<size_t>(own, 1) * m0 * sizeof(uint32_t), ix->gpu, &why) != cudaSuccess)
+      return bail(fail(SHN_ERR_CUDA, "allocating this GPU's share: %s failed", why));
+    ix->d_own_vec = static_cast<float4*>(ix->own_vec_blk.ptr);
+    ix->d_own_l0 = static_cast<uint32_t*>(ix->own_l0_blk.ptr);
+  }
   CUB(cudaMalloc(&ix->d_part_vec, 8 * sizeof(void*)));
   CUB(cudaMalloc(&ix->d_part_l0, 8 * sizeof(void*)));
   CUB(cudaMemset(ix->d_part_vec, 0, 8 * sizeof(void*)));
@@ -672,38 +677,57 @@ int shn_index_partition(shn_index** out, const shn_index* full, int rank, int wo
   return SHN_OK;
 }
 
-int shn_index_partition_export(const shn_index* ix, void* handles, uint64_t* raw_ptrs) {
+int shn_index_partition_export(const shn_index* ix, int* fds, uint64_t* sizes, uint64_t* raw_ptrs) {
   if (!ix || ix->world < 2) return fail(SHN_ERR_STATE, "not a partitioned handle");
   CU(cudaSetDevice(ix->gpu));
-  if (handles) {
-    cudaIpcMemHandle_t h[2];
-    CU(cudaIpcGetMemHandle(&h[0], ix->d_own_vec));
-    CU(cudaIpcGetMemHandle(&h[1], ix->d_own_l0));
-    std::memcpy(handles, h, sizeof h);
+  if (fds) {
+    const char* why = "";
+    if (vmm_export_fd(ix->own_vec_blk, &fds[0], &why) != cudaSuccess || vmm_export_fd(ix->own_l0_blk, &fds[1], &why) != cudaSuccess)
+      return fail(SHN_ERR_CUDA, "exporting the share: %s failed", why);
   }
+  if (sizes) { sizes[0] = ix->own_vec_blk.size; sizes[1] = ix->own_l0_blk.size; }
   if (raw_ptrs) { raw_ptrs[0] = reinterpret_cast<uint64_t>(ix->d_own_vec); raw_ptrs[1] = reinterpret_cast<uint64_t>(ix->d_own_l0); }
   return SHN_OK;
 }
 
-int shn_index_partition_attach(shn_index* ix, int peer, const void* handles, const uint64_t* raw_ptrs) {
+int shn_index_partition_attach(shn_index* ix, int peer, const int* fds, const uint64_t* sizes, const uint64_t* raw_ptrs) {
   if (!ix || ix->world < 2) return fail(SHN_ERR_STATE, "not a partitioned handle");
   if (peer < 0 || peer >= static_cast<int>(ix->world) || peer == static_cast<int>(ix->rank)) return fail(SHN_ERR_ARG, "bad peer rank %d", peer);
-  if (!handles && !raw_ptrs) return fail(SHN_ERR_ARG, "need IPC handles or raw pointers");
+  if (!raw_ptrs && !(fds && sizes)) return fail(SHN_ERR_ARG, "need file descriptors with sizes, or raw pointers");
   CU(cudaSetDevice(ix->gpu));
   void *vp = nullptr, *lp = nullptr;
   if (raw_ptrs) {  // same process (tests, single-process multi-GPU): the pointers are usable as they are
     vp = reinterpret_cast<void*>(raw_ptrs[0]); lp = reinterpret_cast<void*>(raw_ptrs[1]);
-  } else {         // another process: map its allocations (NVLink peer access is enabled by the open)
-    cudaIpcMemHandle_t h[2];
-    std::memcpy(h, handles, sizeof h);
-    CU(cudaIpcOpenMemHandle(&vp, h[0], cudaIpcMemLazyEnablePeerAccess));
-    CU(cudaIpcOpenMemHandle(&lp, h[1], cudaIpcMemLazyEnablePeerAccess));
-    ix->peer_vec[peer] = vp; ix->peer_l0[peer] = lp;
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, vp) == cudaSuccess && attr.type == cudaMemoryTypeDevice && attr.device != ix->gpu) {
+      const cudaError_t pe = cudaDeviceEnablePeerAccess(attr.device, 0);  // the share lives on another GPU of this process
+      if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) return fail(SHN_ERR_CUDA, "peer access to GPU %d: %s", attr.device, cudaGetErrorString(pe));
+      cudaGetLastError();
+    }
+  } else {         // another process: map its physical allocations into this GPU's address space (loads go over NVLink)
+    const char* why = "";
+    if (vmm_import_fd(ix->peer_vec_blk[peer], fds[0], sizes[0], ix->gpu, &why) != cudaSuccess ||
+        vmm_import_fd(ix->peer_l0_blk[peer], fds[1], sizes[1], ix->gpu, &why) != cudaSuccess)
+      return fail(SHN_ERR_CUDA, "mapping the share of rank %d: %s failed", peer, why);
+    vp = ix->peer_vec_blk[peer].ptr; lp = ix->peer_l0_blk[peer].ptr;
   }
   CU(cudaMemcpy(ix->d_part_vec + peer, &vp, sizeof(void*), cudaMemcpyHostToDevice));
   CU(cudaMemcpy(ix->d_part_l0 + peer, &lp, sizeof(void*), cudaMemcpyHostToDevice));
   ++ix->attached;
   return SHN_OK;
+}
+
+// Diagnostic (not in include/shn.h): bandwidth of random whole-row reads from partition `part` as this GPU sees it.
+double shn_debug_partition_gather_gbs(shn_index* ix, int part) {
+  if (!ix || ix->world < 2 || part < 0 || part >= static_cast<int>(ix->world)) return -1.0;
+  cudaSetDevice(ix->gpu);
+  const float4* ptr = nullptr;
+  if (cudaMemcpy(&ptr, ix->d_part_vec + part, sizeof ptr, cudaMemcpyDeviceToHost) != cudaSuccess || !ptr) return -1.0;
+  const uint32_t cold = ix->n - ix->hot;
+  const uint32_t rows = cold > static_cast<uint32_t>(part) ? (cold - part + ix->world - 1) / ix->world : 0;
+  double gbs = -1.0;
+  if (rows == 0 || probe_gather(ptr, rows, ix->row_f4, &gbs, ix->stream) != cudaSuccess) return -1.0;
+  return gbs;
 }
 
 int shn_bruteforce_topk_device(const float* d_base, uint64_t n, const float* d_queries, uint64_t nq, uint32_t dim,

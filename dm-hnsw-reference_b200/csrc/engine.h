@@ -62,6 +62,7 @@ struct PartitionJob {
   uint32_t *hot_l0 = nullptr, *own_l0 = nullptr, *hot_up_base = nullptr, *up = nullptr, *ext_id = nullptr;
 };
 cudaError_t partition_arrays(const PartitionJob& job, cudaStream_t stream);
+cudaError_t probe_gather(const float4* src, uint32_t nrows, uint32_t row_f4, double* gbs, cudaStream_t stream);
 
 // ---- construction (build.cu) ------------------------------------------------------------------------------------
 struct BuildJob {

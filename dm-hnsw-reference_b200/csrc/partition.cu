@@ -48,6 +48,20 @@ __global__ void gather_u32_kernel(const uint32_t* __restrict__ src, const uint32
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) dst[i] = src[old_of_new[i]];
 }
 
+// diagnostic: random whole-row reads from one share (local or peer-mapped)
+__global__ void probe_gather_kernel(const float4* __restrict__ src, uint32_t nrows, uint32_t row_f4, uint32_t iters, float* out) {
+  const int lane = threadIdx.x & 31, t = lane & 7, grp = lane >> 3;
+  uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) / 8 * 2654435761u + 12345u;
+  float acc = 0.f;
+  for (uint32_t it = 0; it < iters; ++it) {
+    s = s * 1664525u + 1013904223u;
+    const uint32_t row = __shfl_sync(0xffffffffu, s, grp * 8) % nrows;
+    const float4* p = src + static_cast<size_t>(row) * row_f4 + t;
+    for (uint32_t b = 0; b < row_f4 / 8; ++b) { const float4 v = __ldg(p + 8 * b); acc += v.x + v.w; }
+  }
+  if (acc == 123.456f) out[0] = acc;
+}
+
 inline int grid_for(uint64_t work, int threads) {
   return static_cast<int>(std::max<uint64_t>(1, std::min<uint64_t>((work + threads - 1) / threads, 148ull * 16)));
 }
@@ -69,6 +83,27 @@ cudaError_t partition_arrays(const PartitionJob& j, cudaStream_t s) {
     gather_lists_kernel<<<grid_for(static_cast<uint64_t>(j.own) * j.m0, 256), 256, 0, s>>>(j.src_l0, j.m0, j.old_of_new, j.new_of_old, hot + j.rank, j.world, j.own, j.own_l0);
   }
   return cudaGetLastError();
+}
+
+
+cudaError_t probe_gather(const float4* src, uint32_t nrows, uint32_t row_f4, double* gbs, cudaStream_t s) {
+  float* out = nullptr;
+  cudaError_t e = cudaMalloc(&out, 4);
+  if (e != cudaSuccess) return e;
+  cudaEvent_t a, b;
+  cudaEventCreate(&a); cudaEventCreate(&b);
+  const int blocks = 148 * 8;
+  const uint32_t iters = 400;
+  probe_gather_kernel<<<blocks, 128, 0, s>>>(src, nrows, row_f4, 20, out);
+  cudaEventRecord(a, s);
+  probe_gather_kernel<<<blocks, 128, 0, s>>>(src, nrows, row_f4, iters, out);
+  cudaEventRecord(b, s);
+  e = cudaStreamSynchronize(s);
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, a, b);
+  *gbs = static_cast<double>(blocks) * 16 * iters * row_f4 * 16.0 / ms / 1e6;
+  cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(out);
+  return e;
 }
 
 }  // namespace shn

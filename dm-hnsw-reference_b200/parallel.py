@@ -47,3 +47,42 @@ def rolling_recall(recall_local, processed_local, n_total, dist=None, device="cp
     if dist is not None:
         dist.all_reduce(t)
     return float(t.item())
+
+
+def exchange_partition_shares(part, rank, world, dist, tag):
+    """Every rank maps every other rank's share: the POSIX fds of the CUDA VMM allocations travel over Unix sockets
+    (SCM_RIGHTS), one listening socket per rank in the abstract namespace."""
+    import os
+    import socket
+    import threading
+    fds, sizes, _ = part.partition_export(want_fds=True)
+    name = lambda r: f"\0shn-share-{tag}-{r}"
+    srv = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+    srv.bind(name(rank))
+    srv.listen(world)
+
+    def serve():
+        for _ in range(world - 1):
+            conn, _ = srv.accept()
+            with conn:
+                msg = f"{sizes[0]} {sizes[1]}".encode()
+                socket.send_fds(conn, [msg], fds)
+
+    th = threading.Thread(target=serve, daemon=True)
+    th.start()
+    dist.barrier()  # every rank is listening
+    for peer in range(world):
+        if peer == rank:
+            continue
+        with socket.socket(socket.AF_UNIX, socket.SOCK_STREAM) as c:
+            c.connect(name(peer))
+            msg, got, _, _ = socket.recv_fds(c, 256, 2)
+        psz = [int(x) for x in msg.decode().split()]
+        part.partition_attach(peer, fds=got, sizes=psz)
+        for fd in got:
+            os.close(fd)  # the import holds its own reference
+    th.join()
+    srv.close()
+    for fd in fds:
+        os.close(fd)
+    dist.barrier()

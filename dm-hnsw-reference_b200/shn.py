@@ -75,8 +75,8 @@ def lib():
         L.shn_index_count_visits.argtypes = [C.c_void_p, C.c_int]
         L.shn_index_visit_counts.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.shn_index_partition.argtypes = [C.POINTER(C.c_void_p), C.c_void_p, C.c_int, C.c_int, C.c_uint32]
-        L.shn_index_partition_export.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]
-        L.shn_index_partition_attach.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_uint64)]
+        L.shn_index_partition_export.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.shn_index_partition_attach.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.shn_set_build_option.argtypes = [C.c_char_p, C.c_int64]
         L.shn_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int64]
         L.shn_search.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p,
@@ -148,16 +148,19 @@ class Index:
         _check(lib().shn_index_partition(C.byref(h), self._h, rank, world, cache_ratio_pct))
         return Index(h, self.metric)
 
-    def partition_export(self):
-        """(128-byte IPC handle blob, (vec_ptr, l0_ptr))"""
-        buf = C.create_string_buffer(128)
+    def partition_export(self, want_fds=False):
+        """(fds or None, sizes, raw pointers): this GPU's share as two POSIX fds (caller closes them) / raw pointers."""
+        fds = (C.c_int * 2)(-1, -1)
+        sizes = (C.c_uint64 * 2)()
         raw = (C.c_uint64 * 2)()
-        _check(lib().shn_index_partition_export(self._h, buf, raw))
-        return buf.raw, (int(raw[0]), int(raw[1]))
+        _check(lib().shn_index_partition_export(self._h, fds if want_fds else None, sizes, raw))
+        return ([int(fds[0]), int(fds[1])] if want_fds else None), [int(sizes[0]), int(sizes[1])], (int(raw[0]), int(raw[1]))
 
-    def partition_attach(self, peer, handles=None, raw_ptrs=None):
+    def partition_attach(self, peer, fds=None, sizes=None, raw_ptrs=None):
         raw = (C.c_uint64 * 2)(*raw_ptrs) if raw_ptrs is not None else None
-        _check(lib().shn_index_partition_attach(self._h, peer, handles, raw))
+        cf = (C.c_int * 2)(*fds) if fds is not None else None
+        cs = (C.c_uint64 * 2)(*sizes) if sizes is not None else None
+        _check(lib().shn_index_partition_attach(self._h, peer, cf, cs, raw))
 
     def build_stats(self):
         st = Stats()

@@ -125,10 +125,13 @@ int shn_index_count_visits(shn_index*, int enable);   /* on: allocate + zero the
 /* copy the counters to (write_back = 0) or from (write_back = 1) a device buffer of n u32 — the caller all-reduces */
 int shn_index_visit_counts(shn_index*, uint32_t* d_counts, int write_back);
 int shn_index_partition(shn_index** out, const shn_index* full, int rank, int world, uint32_t cache_ratio_pct);
-/* handles: 128 bytes out (two cudaIpcMemHandle_t: vectors, level-0 lists) to send to the peers; raw_ptrs: 2 x u64 */
-int shn_index_partition_export(const shn_index*, void* handles, uint64_t* raw_ptrs);
-/* handles from rank `peer` (another process), or its raw pointers (same process).  Search needs every peer attached. */
-int shn_index_partition_attach(shn_index*, int peer, const void* handles, const uint64_t* raw_ptrs);
+/* This GPU's share as two POSIX file descriptors (vectors, level-0 lists; CUDA virtual-memory-management export — the
+ * caller passes them to the other processes over a Unix socket and closes them), their mapped sizes, and the raw device
+ * pointers (for peers inside the same process).  Any of the three outputs may be NULL. */
+int shn_index_partition_export(const shn_index*, int* fds /*2*/, uint64_t* sizes /*2*/, uint64_t* raw_ptrs /*2*/);
+/* Attach rank `peer`'s share: fds + sizes received from another process, or raw_ptrs of a handle in this process.
+ * Searching needs every peer attached. */
+int shn_index_partition_attach(shn_index*, int peer, const int* fds, const uint64_t* sizes, const uint64_t* raw_ptrs);
 
 /* ---- search ------------------------------------------------------------------------------------------------ */
 

@@ -16,7 +16,7 @@ def make_parts(full, world, ratio):
     for r, p in enumerate(parts):
         for peer in range(world):
             if peer != r:
-                p.partition_attach(peer, raw_ptrs=exports[peer][1])
+                p.partition_attach(peer, raw_ptrs=exports[peer][2])
     return parts
 
 
