@@ -192,6 +192,9 @@ def main():
     ap.add_argument("--index-mode", default="replica", choices=["replica", "partitioned"],
                     help="N > 1: every GPU holds the whole index (default) or 1/N of it plus a replicated hot set, "
                          "the rest read over NVLink (SURVEY 8e)")
+    ap.add_argument("--placement", default="scatter", choices=["scatter", "cluster"],
+                    help="partitioned: cold nodes dealt round-robin (the reference's uniform scatter) or stored on the GPU of "
+                         "their nearest k-means centroid, with queries routed to the GPU of theirs (SURVEY 8 f2)")
     ap.add_argument("--cache-ratio", type=int, default=5, help="partitioned: hot set in %% of the nodes (--cache-ratio of the reference)")
     args = ap.parse_args()
     if args.warmup < 3:
@@ -234,13 +237,21 @@ def main():
         dist.all_reduce(counts)
         ix.visit_counts(counts.data_ptr(), write_back=True)
         torch.cuda.synchronize()
-        part = ix.partition(rank, world, args.cache_ratio)
+        centroids = None
+        d_owner = 0
+        if args.placement == "cluster":
+            owner = torch.empty(ix.n, dtype=torch.uint8, device=dev)
+            centroids, sizes = ix.placement_fit(world, owner.data_ptr(), seed=1234, slack=0.05)  # same on every rank
+            d_owner = owner.data_ptr()
+            log(f"[rank {rank}] placement by cluster: part sizes {sizes.tolist()}")
+        part = ix.partition(rank, world, args.cache_ratio, d_owner=d_owner)
         ix.close()
         del counts, warm, tmp_i
+        owner = None
         par_mod = pkg.parallel
         par_mod.exchange_partition_shares(part, rank, world, dist, os.environ.get("MASTER_PORT", "0"))
         ix = part
-        how += f"; partitioned x{world}, hot set {args.cache_ratio}% replicated, peers' shares mapped through CUDA VMM file descriptors ({time.time() - t0:.1f}s)"
+        how += f"; partitioned x{world} ({args.placement}), hot set {args.cache_ratio}% replicated, peers' shares mapped through CUDA VMM file descriptors ({time.time() - t0:.1f}s)"
         log(f"[rank {rank}] {how}; hbm={ix.hbm_bytes / 1e9:.2f} GB")
 
     # query batches: held-out draws of the same model; each rank its own shard (seed), 4 distinct batches rotate
@@ -297,11 +308,28 @@ def main():
         return
 
     # ---- device-resident timing (value) ------------------------------------------------------------------------
-    def step_device(i):
-        return ix.search_device(batches[i % n_batches].data_ptr(), nq, K, ef, ids.data_ptr(), dists.data_ptr(),
-                                stream=stream, want_stats=False)
-
     par = pkg.parallel
+    routed = partitioned and args.placement == "cluster"
+    route_stats = dict(remote=0, total=0)
+
+    def step_device(i):
+        q = batches[i % n_batches]
+        if not routed:
+            return ix.search_device(q.data_ptr(), nq, K, ef, ids.data_ptr(), dists.data_ptr(), stream=stream, want_stats=False)
+        # route every query to the GPU of its nearest centroid, search there, bring the results home
+        torch.cuda.current_stream().synchronize()
+        dest = pkg.route_queries(centroids, q.data_ptr(), nq, ip=wl["ip"], slack=0.25, gpu=local_rank)
+        ex = par.RoutedExchange(dest, world, dist, dev)
+        mine = ex.forward(q)
+        m = mine.shape[0]
+        r_ids = torch.empty((m, K), dtype=torch.int32, device=dev)
+        r_d = torch.empty((m, K), dtype=torch.float32, device=dev)
+        st_r = ix.search_device(mine.data_ptr(), m, K, ef, r_ids.data_ptr(), r_d.data_ptr(), stream=stream)
+        route_stats["remote"] += st_r["rows_remote"]
+        route_stats["total"] += st_r["rows_hot"] + st_r["rows_local"] + st_r["rows_remote"]
+        ids.copy_(ex.backward(r_ids))
+        dists.copy_(ex.backward(r_d))
+        return st_r
 
     def gather():  # per-GPU top-k lists -> every rank, global query order; one all-gather
         return par.allgather_results(ids, dists, world * nq, rank, world, dist)
@@ -345,7 +373,11 @@ def main():
     if partitioned:
         tot = max(1, st["rows_hot"] + st["rows_local"] + st["rows_remote"])
         remote_bytes = st["rows_remote"] * (4 * wl["dim"]) + (st["rows_remote"] / tot) * st["lists_l0"] * 8 * wl["m"]
-        placement = dict(rows_hot=st["rows_hot"] / tot, rows_local=st["rows_local"] / tot, rows_remote=st["rows_remote"] / tot,
+        if routed and route_stats["total"]:
+            placement_note = dict(routed_rows_remote=route_stats["remote"] / route_stats["total"])
+        else:
+            placement_note = {}
+        placement = dict(**placement_note, rows_hot=st["rows_hot"] / tot, rows_local=st["rows_local"] / tot, rows_remote=st["rows_remote"] / tot,
                          nvlink_in_gbs=round(remote_bytes / (kern_ms[-1] * 1e-3) / 1e9, 1), nvlink_peak_gbs=770.0)
 
     # ---- end to end through the host-buffer C-ABI call (e2e) -------------------------------------------------------

@@ -78,7 +78,8 @@ struct shn_index {
   uint32_t vis_cap = 0;
   shn_stats build_stats{};
   // partitioned handle (shn_index_partition): d_vec / d_l0 / d_up_base hold the replicated hot set
-  uint32_t hot = 0, world = 1, rank = 0, own = 0, attached = 1;
+  uint32_t hot = 0, world = 1, rank = 0, own = 0, attached = 1, clustered = 0;
+  uint32_t part_begin[9] = {0};
   float4* d_own_vec = nullptr;
   uint32_t* d_own_l0 = nullptr;
   const float4** d_part_vec = nullptr;   // device table [world]
@@ -94,6 +95,8 @@ struct shn_index {
     g.n = n; g.dim = dim; g.m = m; g.m0 = 2 * m; g.row_f4 = row_f4; g.ep_row = ep_row; g.ep_level = max_level_of_ep;
     g.hot = world > 1 ? hot : n; g.world = world; g.rank = rank;
     g.part_vec = d_part_vec; g.part_l0 = d_part_l0; g.visit_count = d_visits;
+    g.clustered = clustered;
+    for (int i = 0; i < 9; ++i) g.part_begin[i] = part_begin[i];
     return g;
   }
   uint32_t max_level_of_ep = 0;
@@ -588,7 +591,8 @@ int shn_index_visit_counts(shn_index* ix, uint32_t* d_counts, int write_back) {
   return SHN_OK;
 }
 
-int shn_index_partition(shn_index** out, const shn_index* full, int rank, int world, uint32_t cache_ratio_pct) {
+int shn_index_partition(shn_index** out, const shn_index* full, int rank, int world, uint32_t cache_ratio_pct,
+                        const uint8_t* d_owner) {
   if (!out || !full) return fail(SHN_ERR_ARG, "null argument");
   if (full->world > 1) return fail(SHN_ERR_STATE, "the handle is already a partition");
   if (world < 2 || world > 8 || rank < 0 || rank >= world) return fail(SHN_ERR_ARG, "need 2 <= world <= 8 and 0 <= rank < world");
@@ -618,13 +622,31 @@ int shn_index_partition(shn_index** out, const shn_index* full, int rank, int wo
     hot += want;
   }
   std::vector<uint32_t> new_of_old(n);
-  {
-    uint32_t next_hot = 0, next_cold = static_cast<uint32_t>(hot);
-    for (uint32_t r = 0; r < n; ++r) new_of_old[r] = is_hot[r] ? next_hot++ : next_cold++;
-  }
   const uint32_t H = static_cast<uint32_t>(hot);
   const uint32_t cold = n - H;
-  const uint32_t own = cold > static_cast<uint32_t>(rank) ? (cold - rank + world - 1) / world : 0;
+  uint32_t own = 0, begins[9];
+  for (auto& b : begins) b = kInvalid;
+  if (d_owner) {  // clustered placement: [hot | rows of GPU 0 | rows of GPU 1 | ...], old order kept inside each range
+    std::vector<uint8_t> owner(n);
+    CU(cudaMemcpy(owner.data(), d_owner, n, cudaMemcpyDeviceToHost));
+    std::vector<uint32_t> next(world + 1, 0);
+    for (uint32_t r = 0; r < n; ++r) {
+      if (is_hot[r]) continue;
+      if (owner[r] >= world) return fail(SHN_ERR_ARG, "owner[%u] = %u is not a rank below %d", r, owner[r], world);
+      ++next[owner[r] + 1];
+    }
+    begins[0] = H;
+    for (int g = 0; g < world; ++g) begins[g + 1] = begins[g] + next[g + 1];
+    own = next[rank + 1];
+    std::vector<uint32_t> cursor(begins, begins + world);
+    uint32_t next_hot = 0;
+    for (uint32_t r = 0; r < n; ++r) new_of_old[r] = is_hot[r] ? next_hot++ : cursor[owner[r]]++;
+    for (int g = world + 1; g < 9; ++g) begins[g] = kInvalid;
+  } else {        // the reference's policy: uniform scatter (compute_thread.hh:57), here round-robin over the cold rows
+    uint32_t next_hot = 0, next_cold = H;
+    for (uint32_t r = 0; r < n; ++r) new_of_old[r] = is_hot[r] ? next_hot++ : next_cold++;
+    own = cold > static_cast<uint32_t>(rank) ? (cold - rank + world - 1) / world : 0;
+  }
 
   shn_index* ix = nullptr;
   int rc = new_handle(&ix, full->gpu, full->metric);
@@ -634,6 +656,8 @@ int shn_index_partition(shn_index** out, const shn_index* full, int rank, int wo
   ix->n = n; ix->dim = full->dim; ix->m = full->m; ix->row_f4 = full->row_f4; ix->n_up = full->n_up; ix->max_level = full->max_level;
   ix->max_level_of_ep = full->max_level_of_ep; ix->ep_row = new_of_old[full->ep_row];
   ix->hot = H; ix->world = world; ix->rank = rank; ix->own = own; ix->attached = 1;
+  ix->clustered = d_owner ? 1u : 0u;
+  for (int i = 0; i < 9; ++i) ix->part_begin[i] = d_owner ? begins[i] : 0u;
   ix->warps_per_sm = full->warps_per_sm; ix->vis_cap = full->vis_cap; ix->dump_bytes = full->dump_bytes;
   const size_t row_bytes = static_cast<size_t>(ix->row_f4) * 16, m0 = 2ull * ix->m;
   uint32_t *d_new_of_old = nullptr, *d_old_of_new = nullptr;
@@ -659,7 +683,8 @@ int shn_index_partition(shn_index** out, const shn_index* full, int rank, int wo
   CUB(cudaMemset(ix->d_part_l0, 0, 8 * sizeof(void*)));
   ix->hbm_bytes = H * (row_bytes + m0 * 4 + 4) + own * (row_bytes + m0 * 4) + n * 4ull + std::max<size_t>(ix->n_up, 1) * ix->m * 4;
   PartitionJob job;
-  job.n = n; job.hot = H; job.own = own; job.rank = rank; job.world = world; job.row_f4 = ix->row_f4; job.m = ix->m; job.m0 = 2 * ix->m;
+  job.n = n; job.hot = H; job.own = own; job.rank = d_owner ? 0 : rank; job.world = d_owner ? 1 : world;
+  job.own_first = d_owner ? begins[rank] : H + rank; job.row_f4 = ix->row_f4; job.m = ix->m; job.m0 = 2 * ix->m;
   job.n_up = ix->n_up; job.new_of_old = d_new_of_old; job.old_of_new = d_old_of_new;
   job.src_vec = full->d_vec; job.src_l0 = full->d_l0; job.src_up_base = full->d_up_base; job.src_up = full->d_up; job.src_ext_id = full->d_ext_id;
   job.hot_vec = ix->d_vec; job.own_vec = ix->d_own_vec; job.hot_l0 = ix->d_l0; job.own_l0 = ix->d_own_l0;
@@ -674,6 +699,95 @@ int shn_index_partition(shn_index** out, const shn_index* full, int rank, int wo
   CUB(cudaMemcpy(ix->d_part_l0 + rank, &lp, sizeof(void*), cudaMemcpyHostToDevice));
 #undef CUB
   *out = ix;
+  return SHN_OK;
+}
+
+int shn_placement_fit(const shn_index* full, int world, uint32_t seed, double slack, float* centroids, uint8_t* d_owner,
+                      uint64_t* part_sizes) {
+  if (!full || !centroids || !d_owner) return fail(SHN_ERR_ARG, "null argument");
+  if (full->world > 1) return fail(SHN_ERR_STATE, "placement is fitted on the full index");
+  if (world < 2 || world > 8) return fail(SHN_ERR_ARG, "need 2 <= world <= 8");
+  CU(cudaSetDevice(full->gpu));
+  CU(cudaStreamSynchronize(full->stream));
+  const uint32_t n = full->n, dimS = full->row_f4 * 4;
+  // sample: the upper-level nodes (placement.hh:78-106 fetches the top levels), topped up with level-0 rows if scarce
+  std::vector<uint32_t> level(n);
+  CU(cudaMemcpy(level.data(), full->d_level, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  std::vector<uint32_t> rows;
+  for (uint32_t r = 0; r < n; ++r) if (level[r] > 0) rows.push_back(r);
+  if (rows.size() > 65536) {
+    std::vector<uint32_t> thin;
+    const double step = static_cast<double>(rows.size()) / 65536;
+    for (uint32_t i = 0; i < 65536; ++i) thin.push_back(rows[static_cast<size_t>(i * step)]);
+    rows.swap(thin);
+  }
+  if (rows.size() < 500) {
+    const uint32_t want = std::min<uint32_t>(n, 4096);
+    const uint32_t stride = std::max<uint32_t>(1, n / want);
+    for (uint32_t r = 0; r < n && rows.size() < want + 500; r += stride) if (level[r] == 0) rows.push_back(r);
+  }
+  if (rows.size() < static_cast<size_t>(world)) return fail(SHN_ERR_ARG, "fewer nodes than partitions");
+  std::vector<float> sample(rows.size() * dimS);
+  for (size_t i = 0; i < rows.size(); ++i)
+    CU(cudaMemcpy(sample.data() + i * dimS, reinterpret_cast<const float*>(full->d_vec) + static_cast<size_t>(rows[i]) * dimS,
+                  dimS * sizeof(float), cudaMemcpyDeviceToHost));
+  std::vector<float> cent;
+  kmeans_host(sample, static_cast<uint32_t>(rows.size()), dimS, world, seed, full->metric == SHN_IP, cent);
+  float* d_cent = nullptr;
+  CU(cudaMalloc(&d_cent, cent.size() * sizeof(float)));
+  CU(cudaMemcpy(d_cent, cent.data(), cent.size() * sizeof(float), cudaMemcpyHostToDevice));
+  std::vector<uint32_t> sizes;
+  cudaError_t e = balanced_assign(full->d_vec, n, full->row_f4, d_cent, world, full->metric == SHN_IP, slack, d_owner, sizes, full->stream);
+  cudaFree(d_cent);
+  if (e != cudaSuccess) return fail(SHN_ERR_CUDA, "balanced_assign: %s", cudaGetErrorString(e));
+  for (int c = 0; c < world; ++c) {
+    if (part_sizes) part_sizes[c] = sizes[c];
+    for (uint32_t j = 0; j < full->dim; ++j) centroids[static_cast<size_t>(c) * full->dim + j] = cent[static_cast<size_t>(c) * dimS + row_pos(full->dim, j)];
+  }
+  return SHN_OK;
+}
+
+int shn_route_queries(const float* centroids, int world, uint32_t dim, shn_metric metric, const float* d_queries, uint64_t nq,
+                      double slack, uint8_t* dest, int gpu_id) {
+  if (!centroids || !d_queries || !dest) return fail(SHN_ERR_ARG, "null argument");
+  if (world < 1 || world > 8 || dim == 0) return fail(SHN_ERR_ARG, "need 1 <= world <= 8");
+  if (nq == 0) return SHN_OK;
+  if (nq >= kInvalid) return fail(SHN_ERR_ARG, "too many queries");
+  int sms = 0;
+  int rc = select_device(gpu_id, &sms);
+  if (rc != SHN_OK) return rc;
+  const uint32_t pad = (dim + 3) / 4 * 4;
+  float *d_cent = nullptr, *d_q = nullptr, *d_dist = nullptr;
+  std::vector<float> cent(static_cast<size_t>(world) * pad, 0.f);
+  for (int c = 0; c < world; ++c) std::memcpy(cent.data() + static_cast<size_t>(c) * pad, centroids + static_cast<size_t>(c) * dim, dim * sizeof(float));
+  cudaError_t e = cudaMalloc(&d_cent, cent.size() * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&d_dist, nq * world * sizeof(float));
+  if (e == cudaSuccess) e = cudaMemcpy(d_cent, cent.data(), cent.size() * sizeof(float), cudaMemcpyHostToDevice);
+  const float* rows = d_queries;
+  if (e == cudaSuccess && pad != dim) {  // rows must be whole float4s
+    e = cudaMalloc(&d_q, nq * pad * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemset(d_q, 0, nq * pad * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemcpy2D(d_q, pad * sizeof(float), d_queries, dim * sizeof(float), dim * sizeof(float), nq, cudaMemcpyDeviceToDevice);
+    rows = d_q;
+  }
+  std::vector<float> dist(nq * world);
+  if (e == cudaSuccess) e = centroid_distances(rows, static_cast<uint32_t>(nq), pad / 4, d_cent, world, metric == SHN_IP, d_dist, nullptr);
+  if (e == cudaSuccess) e = cudaMemcpy(dist.data(), d_dist, dist.size() * sizeof(float), cudaMemcpyDeviceToHost);
+  cudaFree(d_cent); cudaFree(d_q); cudaFree(d_dist);
+  if (e != cudaSuccess) return fail(SHN_ERR_CUDA, "routing: %s", cudaGetErrorString(e));
+  // query_router.hh:356-368: the nearest centroid whose compute node is under its limit for this batch
+  const uint64_t limit = static_cast<uint64_t>((1.0 + slack) * static_cast<double>(nq) / world) + 1;
+  std::vector<uint64_t> histogram(world, 0);
+  for (uint64_t q = 0; q < nq; ++q) {
+    int order[9];
+    for (int c = 0; c < world; ++c) order[c] = c;
+    const float* dq = dist.data() + q * world;
+    std::sort(order, order + world, [&](int a, int b) { return dq[a] != dq[b] ? dq[a] < dq[b] : a < b; });
+    int pick = order[world - 1];
+    for (int c = 0; c < world; ++c) if (histogram[order[c]] < limit) { pick = order[c]; break; }
+    ++histogram[pick];
+    dest[q] = static_cast<uint8_t>(pick);
+  }
   return SHN_OK;
 }
 
@@ -724,7 +838,8 @@ double shn_debug_partition_gather_gbs(shn_index* ix, int part) {
   const float4* ptr = nullptr;
   if (cudaMemcpy(&ptr, ix->d_part_vec + part, sizeof ptr, cudaMemcpyDeviceToHost) != cudaSuccess || !ptr) return -1.0;
   const uint32_t cold = ix->n - ix->hot;
-  const uint32_t rows = cold > static_cast<uint32_t>(part) ? (cold - part + ix->world - 1) / ix->world : 0;
+  const uint32_t rows = ix->clustered ? ix->part_begin[part + 1] - ix->part_begin[part]
+                                      : (cold > static_cast<uint32_t>(part) ? (cold - part + ix->world - 1) / ix->world : 0);
   double gbs = -1.0;
   if (rows == 0 || probe_gather(ptr, rows, ix->row_f4, &gbs, ix->stream) != cudaSuccess) return -1.0;
   return gbs;

@@ -53,6 +53,7 @@ cudaError_t rows_from_layout(const float* d_src, float* d_dst, uint64_t n, uint3
 // ---- partitioning (partition.cu)
 struct PartitionJob {
   uint32_t n = 0, hot = 0, own = 0, rank = 0, world = 1, row_f4 = 0, m = 0, m0 = 0;
+  uint32_t own_first = 0;  // new id of this GPU's first own row; its rows are own_first + i * world
   uint64_t n_up = 0;
   const uint32_t* new_of_old = nullptr;  // [n] device
   uint32_t* old_of_new = nullptr;        // [n] device scratch
@@ -63,6 +64,15 @@ struct PartitionJob {
 };
 cudaError_t partition_arrays(const PartitionJob& job, cudaStream_t stream);
 cudaError_t probe_gather(const float4* src, uint32_t nrows, uint32_t row_f4, double* gbs, cudaStream_t stream);
+
+// ---- placement and routing (placement.cu)
+void kmeans_host(const std::vector<float>& sample, uint32_t count, uint32_t d, int k, uint32_t seed, bool ip,
+                 std::vector<float>& centroids);
+cudaError_t balanced_assign(const float4* d_vec, uint32_t n, uint32_t row_f4, const float* d_cent_stored, int k, bool ip,
+                            double slack, uint8_t* d_owner, std::vector<uint32_t>& sizes, cudaStream_t s);
+// rows of row_f4 float4 (any consistent element order) against k centroids of the same width -> out[n][k]
+cudaError_t centroid_distances(const float* d_rows, uint32_t n, uint32_t row_f4, const float* d_cent, int k, bool ip,
+                               float* d_out, cudaStream_t s);
 
 // ---- construction (build.cu) ------------------------------------------------------------------------------------
 struct BuildJob {

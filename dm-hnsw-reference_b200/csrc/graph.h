@@ -87,21 +87,41 @@ struct DeviceGraph {
   uint32_t row_f4;    // row stride of vec in float4
   uint32_t ep_row, ep_level;
   uint32_t hot, world, rank;
+  uint32_t clustered;       // 0: row r >= hot lives on GPU (r-hot) % world; 1: GPU p owns rows [part_begin[p], part_begin[p+1])
+  uint32_t part_begin[9];   // clustered placement (placement.cu); entries beyond `world` are 0xFFFFFFFF
   const float4* const* part_vec;
   const uint32_t* const* part_l0;
   uint32_t* visit_count;  // optional [n]: +1 per level-0 distance computation (warm-up pass that picks the hot set)
 };
 
 #ifdef __CUDACC__
+// owner GPU and local index of a row that is not in the replicated hot set
+__device__ __forceinline__ void locate_row(const DeviceGraph& g, uint32_t row, uint32_t& part, uint32_t& idx) {
+  if (g.clustered) {
+    part = 0;
+    uint32_t begin = g.part_begin[0];
+#pragma unroll
+    for (int j = 1; j < 8; ++j) {
+      if (row >= g.part_begin[j]) { part = j; begin = g.part_begin[j]; }
+    }
+    idx = row - begin;
+  } else {
+    const uint32_t o = row - g.hot;
+    part = o % g.world;
+    idx = o / g.world;
+  }
+}
 __device__ __forceinline__ const float4* vec_row(const DeviceGraph& g, uint32_t row) {
   if (row < g.hot) return g.vec + static_cast<size_t>(row) * g.row_f4;
-  const uint32_t o = row - g.hot;
-  return g.part_vec[o % g.world] + static_cast<size_t>(o / g.world) * g.row_f4;
+  uint32_t part, idx;
+  locate_row(g, row, part, idx);
+  return g.part_vec[part] + static_cast<size_t>(idx) * g.row_f4;
 }
 __device__ __forceinline__ const uint32_t* l0_row(const DeviceGraph& g, uint32_t row) {
   if (row < g.hot) return g.l0 + static_cast<size_t>(row) * g.m0;
-  const uint32_t o = row - g.hot;
-  return g.part_l0[o % g.world] + static_cast<size_t>(o / g.world) * g.m0;
+  uint32_t part, idx;
+  locate_row(g, row, part, idx);
+  return g.part_l0[part] + static_cast<size_t>(idx) * g.m0;
 }
 #endif
 

@@ -79,8 +79,8 @@ cudaError_t partition_arrays(const PartitionJob& j, cudaStream_t s) {
   gather_u32_kernel<<<grid_for(n, 256), 256, 0, s>>>(j.src_ext_id, j.old_of_new, n, j.ext_id);
   // this GPU's share of the remaining rows: new ids hot + rank, hot + rank + world, ...
   if (j.own) {
-    gather_rows_kernel<<<grid_for(static_cast<uint64_t>(j.own) * 32, 256), 256, 0, s>>>(j.src_vec, j.old_of_new, hot + j.rank, j.world, j.own, j.row_f4, j.own_vec);
-    gather_lists_kernel<<<grid_for(static_cast<uint64_t>(j.own) * j.m0, 256), 256, 0, s>>>(j.src_l0, j.m0, j.old_of_new, j.new_of_old, hot + j.rank, j.world, j.own, j.own_l0);
+    gather_rows_kernel<<<grid_for(static_cast<uint64_t>(j.own) * 32, 256), 256, 0, s>>>(j.src_vec, j.old_of_new, j.own_first, j.world, j.own, j.row_f4, j.own_vec);
+    gather_lists_kernel<<<grid_for(static_cast<uint64_t>(j.own) * j.m0, 256), 256, 0, s>>>(j.src_l0, j.m0, j.old_of_new, j.new_of_old, j.own_first, j.world, j.own, j.own_l0);
   }
   return cudaGetLastError();
 }

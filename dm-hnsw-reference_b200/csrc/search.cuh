@@ -469,7 +469,9 @@ __device__ __forceinline__ void beam_search(const DeviceGraph& g, const float* s
         const bool in = i < cnt;
         if (in && g.visit_count) atomicAdd(g.visit_count + row, 1u);
         const bool hot = in && row < g.hot;
-        const bool mine = in && !hot && (row - g.hot) % g.world == g.rank;
+        uint32_t part = 0, idx = 0;
+        if (in && !hot) locate_row(g, row, part, idx);
+        const bool mine = in && !hot && part == g.rank;
         c_hot += __popc(__ballot_sync(kFull, hot));
         c_local += __popc(__ballot_sync(kFull, mine));
       }

@@ -86,3 +86,34 @@ def exchange_partition_shares(part, rank, world, dist, tag):
     for fd in fds:
         os.close(fd)
     dist.barrier()
+
+
+class RoutedExchange:
+    """Query routing between ranks (the reference: QueryRouter::route_query / poll_recv_cq relayed through memory nodes,
+    src/router/query_router.hh:83-104,195-210): rows travel to the rank `dest` names with ONE all-to-all(v), results come
+    back with a second one and are put back in the caller's order.  Works on CPU (gloo) and GPU (nccl) tensors."""
+
+    def __init__(self, dest, world, dist, device):
+        self.world, self.dist = world, dist
+        dest = torch.as_tensor(dest, dtype=torch.int64, device=device)
+        self.order = torch.argsort(dest, stable=True)
+        self.send_counts = torch.bincount(dest, minlength=world)
+        recv = torch.empty_like(self.send_counts)
+        dist.all_to_all_single(recv, self.send_counts)
+        self.recv_counts = recv
+        self.send_list = self.send_counts.tolist()
+        self.recv_list = self.recv_counts.tolist()
+
+    def forward(self, rows):
+        """rows [n, ...] in the caller's order -> the rows this rank has to process."""
+        out = torch.empty((sum(self.recv_list),) + tuple(rows.shape[1:]), dtype=rows.dtype, device=rows.device)
+        self.dist.all_to_all_single(out, rows[self.order].contiguous(), self.recv_list, self.send_list)
+        return out
+
+    def backward(self, results):
+        """results [n_received, ...] -> results for the caller's own rows, in the caller's order."""
+        back = torch.empty((sum(self.send_list),) + tuple(results.shape[1:]), dtype=results.dtype, device=results.device)
+        self.dist.all_to_all_single(back, results.contiguous(), self.send_list, self.recv_list)
+        out = torch.empty_like(back)
+        out[self.order] = back
+        return out

@@ -74,7 +74,9 @@ def lib():
                                                  C.c_uint32, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.shn_index_count_visits.argtypes = [C.c_void_p, C.c_int]
         L.shn_index_visit_counts.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
-        L.shn_index_partition.argtypes = [C.POINTER(C.c_void_p), C.c_void_p, C.c_int, C.c_int, C.c_uint32]
+        L.shn_index_partition.argtypes = [C.POINTER(C.c_void_p), C.c_void_p, C.c_int, C.c_int, C.c_uint32, C.c_void_p]
+        L.shn_placement_fit.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.shn_route_queries.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_int, C.c_void_p, C.c_uint64, C.c_double, C.c_void_p, C.c_int]
         L.shn_index_partition_export.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.shn_index_partition_attach.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.shn_set_build_option.argtypes = [C.c_char_p, C.c_int64]
@@ -143,10 +145,18 @@ class Index:
         """Copy the per-node visit counters to / from a device buffer of n u32 (raw pointer)."""
         _check(lib().shn_index_visit_counts(self._h, d_counts, int(write_back)))
 
-    def partition(self, rank, world, cache_ratio_pct=5):
+    def partition(self, rank, world, cache_ratio_pct=5, d_owner=0):
+        """d_owner: device pointer to n bytes from placement_fit (placement by cluster); 0 = round-robin."""
         h = C.c_void_p()
-        _check(lib().shn_index_partition(C.byref(h), self._h, rank, world, cache_ratio_pct))
+        _check(lib().shn_index_partition(C.byref(h), self._h, rank, world, cache_ratio_pct, d_owner or None))
         return Index(h, self.metric)
+
+    def placement_fit(self, world, d_owner, seed=1234, slack=0.05):
+        """k-means over the upper-level nodes + balanced assignment of every node; returns (centroids [world,dim], sizes)."""
+        cent = np.empty((world, self.dim), np.float32)
+        sizes = np.zeros(world, np.uint64)
+        _check(lib().shn_placement_fit(self._h, world, seed, slack, cent.ctypes.data, d_owner, sizes.ctypes.data))
+        return cent, sizes
 
     def partition_export(self, want_fds=False):
         """(fds or None, sizes, raw pointers): this GPU's share as two POSIX fds (caller closes them) / raw pointers."""
@@ -273,3 +283,12 @@ def bruteforce_topk(base, queries, k, ip=False, gpu=0):
 def bruteforce_topk_device(d_base, n, d_queries, nq, dim, k, d_ids, d_dists=0, ip=False, gpu=0, stream=0):
     _check(lib().shn_bruteforce_topk_device(d_base, n, d_queries, nq, dim, IP if ip else L2, k, d_ids, d_dists or None, gpu,
                                             stream or None))
+
+
+def route_queries(centroids, d_queries, nq, ip=False, slack=0.25, gpu=0):
+    """dest[q] = rank of the nearest centroid still under its share of the batch (host uint8 array)."""
+    c = np.ascontiguousarray(centroids, dtype=np.float32)
+    dest = np.empty(nq, np.uint8)
+    _check(lib().shn_route_queries(c.ctypes.data, c.shape[0], c.shape[1], IP if ip else L2, d_queries, nq, slack,
+                                   dest.ctypes.data, gpu))
+    return dest

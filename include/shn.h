@@ -124,7 +124,20 @@ int shn_set_option(shn_index*, const char* key, int64_t value);
 int shn_index_count_visits(shn_index*, int enable);   /* on: allocate + zero the per-node counters; searches then count */
 /* copy the counters to (write_back = 0) or from (write_back = 1) a device buffer of n u32 — the caller all-reduces */
 int shn_index_visit_counts(shn_index*, uint32_t* d_counts, int write_back);
-int shn_index_partition(shn_index** out, const shn_index* full, int rank, int world, uint32_t cache_ratio_pct);
+/* d_owner == NULL: cold rows dealt round-robin (the reference's uniform scatter).  d_owner = device array of n bytes,
+ * owner[row] < world (from shn_placement_fit): rank p keeps exactly the cold rows it owns. */
+int shn_index_partition(shn_index** out, const shn_index* full, int rank, int world, uint32_t cache_ratio_pct,
+                        const uint8_t* d_owner);
+/* Placement by cluster + query routing (the reference: Placement src/cache/placement.hh:22-106, balanced k-means
+ * src/cache/kmeans.hh:24-377 with k = #compute nodes, router src/router/query_router.hh:280-387).  Fit: k-means
+ * (k-means++ from mt19937(seed)) over the upper-level nodes, then every node goes to the GPU of its nearest centroid with
+ * no GPU more than (1 + slack) * n / world nodes.  centroids: host [world][dim] out; d_owner: device [n] out. */
+int shn_placement_fit(const shn_index* full, int world, uint32_t seed, double slack, float* centroids, uint8_t* d_owner,
+                      uint64_t* part_sizes /*[world], may be NULL*/);
+/* dest[q] = the rank query q should run on: its nearest centroid whose rank is still under (1 + slack) * nq / world
+ * queries of this batch, in query order (query_router.hh:356-368).  d_queries: device [nq][dim]; dest: host [nq]. */
+int shn_route_queries(const float* centroids, int world, uint32_t dim, shn_metric metric, const float* d_queries, uint64_t nq,
+                      double slack, uint8_t* dest, int gpu_id);
 /* This GPU's share as two POSIX file descriptors (vectors, level-0 lists; CUDA virtual-memory-management export — the
  * caller passes them to the other processes over a Unix socket and closes them), their mapped sizes, and the raw device
  * pointers (for peers inside the same process).  Any of the three outputs may be NULL. */

@@ -55,3 +55,34 @@ def test_shard_slots_partition():
             parts = [par.shard_slots(n, r, world) for r in range(world)]
             assert sorted(np.concatenate(parts).tolist()) == list(range(n))
             assert [len(p) for p in parts] == [par.shard_size(n, r, world) for r in range(world)]
+
+
+def _route_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as ge
+    par = ge.load_package().parallel
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(100 + rank)
+    n = 500 + 37 * rank
+    rows = torch.from_numpy(rng.random((n, 6)).astype(np.float32))
+    dest = rng.integers(0, world, n)
+    if rank == 0:
+        dest[:] = world - 1  # everything leaves rank 0
+    ex = par.RoutedExchange(dest, world, dist, "cpu")
+    got = ex.forward(rows)
+    assert got.shape[0] == sum(ex.recv_list)
+    res = torch.stack([got.sum(1), got[:, 0] * 2 + rank * 0], 1)  # "search": a function of the row only
+    back = ex.backward(res)
+    ok = bool(torch.allclose(back[:, 0], rows.sum(1)) and torch.allclose(back[:, 1], rows[:, 0] * 2))
+    with open(os.path.join(out_dir, f"r{rank}"), "w") as f:
+        f.write("ok" if ok else "bad")
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_routed_exchange_round_trip(tmp_path, world):
+    port = 31500 + (os.getpid() + world * 11) % 2000
+    mp.spawn(_route_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        assert open(tmp_path / f"r{r}").read() == "ok"

@@ -66,3 +66,46 @@ def test_partition_state_errors(pkg):
         with pytest.raises(pkg.ShnError):
             p0.partition_attach(0, raw_ptrs=(1, 1))
         p0.close()
+
+
+@pytest.mark.parametrize("world,ip", [(4, False), (2, True)])
+def test_placement_by_cluster_and_routing(pkg, world, ip):
+    """Nodes stored on the GPU of their nearest centroid, queries run on the GPU of theirs: same results, and most
+    level-0 reads become local (the point of the reference's Placement + QueryRouter)."""
+    import torch
+    n, dim = 30000, 32
+    base, queries = datagen.base_and_queries(n, 800, dim, normalize=ip)
+    with pkg.Index.build(base, 16, 100, ip=ip) as full:
+        ref = full.search(queries, 10, 64)
+        owner = torch.empty(n, dtype=torch.uint8, device="cuda")
+        cent, sizes = full.placement_fit(world, owner.data_ptr(), slack=0.05)
+        assert sizes.sum() == n and sizes.max() <= 1.06 * n / world + 1 and cent.shape == (world, dim)
+        assert (torch.bincount(owner.long(), minlength=world).cpu().numpy() == sizes).all()
+        clustered = [full.partition(r, world, 0, d_owner=owner.data_ptr()) for r in range(world)]
+        scattered = [full.partition(r, world, 0) for r in range(world)]
+    for group in (clustered, scattered):
+        ex = [p.partition_export() for p in group]
+        for r, p in enumerate(group):
+            for peer in range(world):
+                if peer != r:
+                    p.partition_attach(peer, raw_ptrs=ex[peer][2])
+    try:
+        q_dev = torch.from_numpy(queries).cuda()
+        dest = pkg.route_queries(cent, q_dev.data_ptr(), len(queries), ip=ip, slack=0.25)
+        assert dest.max() < world and np.bincount(dest, minlength=world).max() <= 1.25 * len(queries) / world + 1
+        remote = {}
+        for name, group in (("clustered", clustered), ("scattered", scattered)):
+            rem = tot = 0
+            for r, p in enumerate(group):
+                mine = np.nonzero(dest == r)[0]
+                if len(mine) == 0:
+                    continue
+                ids, dists, st = p.search(queries[mine], 10, 64)
+                assert (ids == ref[0][mine]).all() and (dists.view(np.uint32) == ref[1][mine].view(np.uint32)).all()
+                rem += st["rows_remote"]; tot += st["rows_hot"] + st["rows_local"] + st["rows_remote"]
+            remote[name] = rem / tot
+        print("remote fraction of level-0 reads:", remote)
+        assert remote["clustered"] < 0.6 * remote["scattered"]
+    finally:
+        for p in clustered + scattered:
+            p.close()
