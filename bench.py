@@ -36,6 +36,15 @@ WORKLOADS = {
     # BASELINE.json configs[0]
     "sift1m": dict(n=1_000_000, dim=128, ip=False, m=16, efc=200, normalize=False,
                    label="SIFT1M-shaped synthetic (1M x 128 fp32, L2, M=16, efC=200), ef sweep 16-256, k=10"),
+    # BASELINE.json configs[4]: Text-to-Image-10M-shaped, inner product, skewed queries (--zipf)
+    "t2i10m": dict(n=10_000_000, dim=200, ip=True, m=16, efc=200, normalize=True,
+                   label="Text-to-Image-10M-shaped synthetic (10M x 200 fp32, inner product, M=16, efC=200), ef sweep 16-256, k=10"),
+    # BASELINE.json configs[3]: GIST1M-shaped, the high-dimensional bandwidth-bound case
+    "gist1m": dict(n=1_000_000, dim=960, ip=False, m=16, efc=200, normalize=False,
+                   label="GIST1M-shaped synthetic (1M x 960 fp32, L2, M=16, efC=200), ef sweep 16-256, k=10"),
+    # BASELINE.json configs[2]: DEEP100M-shaped
+    "deep100m": dict(n=100_000_000, dim=96, ip=False, m=16, efc=200, normalize=True,
+                     label="DEEP100M-shaped synthetic (100M x 96 fp32 unit rows, L2, M=16, efC=200), ef sweep 16-256, k=10"),
     "tiny": dict(n=100_000, dim=128, ip=False, m=16, efc=200, normalize=False,
                  label="100k x 128 fp32 synthetic (smoke-sized), L2, M=16, efC=200"),
 }
@@ -192,6 +201,9 @@ def main():
     ap.add_argument("--index-mode", default="replica", choices=["replica", "partitioned"],
                     help="N > 1: every GPU holds the whole index (default) or 1/N of it plus a replicated hot set, "
                          "the rest read over NVLink (SURVEY 8e)")
+    ap.add_argument("--zipf", type=float, default=None,
+                    help="skew the queries: a pool of 100k distinct queries expanded with Zipf(alpha) popularity exactly as the "
+                         "reference's scripts/data/skew.py; the hot-set warm-up then uses queries of the same distribution")
     ap.add_argument("--placement", default="scatter", choices=["scatter", "cluster"],
                     help="partitioned: cold nodes dealt round-robin (the reference's uniform scatter) or stored on the GPU of "
                          "their nearest k-means centroid, with queries routed to the GPU of theirs (SURVEY 8 f2)")
@@ -228,7 +240,14 @@ def main():
         # warm-up pass with visit counting -> the same hot set on every rank -> keep 1/world of the cold rows and map
         # the peers' shares (CUDA IPC handles travel over torch.distributed, the loads then go over NVLink)
         t0 = time.time()
-        warm = synth_rows(min(nq, 200_000), wl["dim"], 7007 + rank, dev, wl["normalize"])
+        def warm_queries(count, seed):
+            if args.zipf is None:
+                return synth_rows(count, wl["dim"], seed, dev, wl["normalize"])
+            import datagen
+            pool = synth_rows(100_000, wl["dim"], 2002, dev, wl["normalize"])
+            return pool[torch.from_numpy(datagen.zipf_indices(100_000, count, args.zipf, seed=seed)).to(dev)].contiguous()
+
+        warm = warm_queries(min(nq, 200_000), 7007 + rank)
         tmp_i = torch.empty((warm.shape[0], K), dtype=torch.int32, device=dev)
         ix.count_visits(True)
         ix.search_device(warm.data_ptr(), warm.shape[0], K, 64, tmp_i.data_ptr())
@@ -256,7 +275,15 @@ def main():
 
     # query batches: held-out draws of the same model; each rank its own shard (seed), 4 distinct batches rotate
     n_batches = 4
-    batches = [synth_rows(nq, wl["dim"], 2002 + 1000 * rank + b, dev, wl["normalize"]) for b in range(n_batches)]
+    def make_queries(count, seed):
+        if args.zipf is None:
+            return synth_rows(count, wl["dim"], seed, dev, wl["normalize"])
+        import datagen
+        pool = synth_rows(100_000, wl["dim"], 2002, dev, wl["normalize"])  # the same pool on every rank
+        pick = torch.from_numpy(datagen.zipf_indices(100_000, count, args.zipf, seed=seed)).to(dev)
+        return pool[pick].contiguous()
+
+    batches = [make_queries(nq, 2002 + 1000 * rank + b) for b in range(n_batches)]
     ids = torch.empty((nq, K), dtype=torch.int32, device=dev)
     dists = torch.empty((nq, K), dtype=torch.float32, device=dev)
     # a non-default torch stream: the C ABI launches on the stream it is handed, and torch.cuda.Event only sees
@@ -421,7 +448,7 @@ def main():
                 steps=args.steps, warmup=args.warmup, ms_per_step=round(total_ms / args.steps, 3), higher_is_better=True,
                 scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
                 config=dict(workload=wl["label"], ef=ef, k=K, recall_at_10=recall, queries_per_step_per_gpu=nq,
-                            index=how, index_build_s=round(build_s, 1), l2_policy="index (>= 6 GB at 10M rows) and the "
+                            index=how, index_build_s=round(build_s, 1), zipf_alpha=args.zipf, l2_policy="index (>= 6 GB at 10M rows) and the "
                             "rotating query batches are larger than the 126 MB L2; no flush",
                             parallelism=(f"{args.index_mode} x{world}, queries sharded, NCCL all-gather of top-k" if world > 1 else "single GPU"),
                             placement=placement),

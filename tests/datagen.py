@@ -36,3 +36,20 @@ def recall(ids, gt):
     for a, b in zip(ids, gt):
         hit += len(set(a.tolist()) & set(b.tolist()))
     return hit / (gt.shape[0] * k)
+
+
+def zipf_indices(pool_size, n, alpha, seed=1234):
+    """Query skew exactly as scripts/data/skew.py:114-153 of the reference: pool entry k (1-based, pool order) is drawn
+    ceil(n * p_k) times with p_k = k^-alpha / H(pool_size, alpha) until n are drawn, then the sequence is shuffled — with a
+    SEEDED permutation (the reference's is unseeded, :153).  alpha = 0 is the uniform distribution."""
+    k = np.arange(1, pool_size + 1, dtype=np.float64)
+    p = k ** -float(alpha)
+    p /= p.sum()
+    occ = np.ceil(n * p).astype(np.int64)
+    cum = np.cumsum(occ)
+    last = int(np.searchsorted(cum, n))            # first pool entry at which >= n have been drawn
+    occ = occ[: last + 1].copy()
+    occ[-1] -= int(cum[last] - n)                    # the reference asserts drawn == n; trim the overshoot instead
+    idx = np.repeat(np.arange(last + 1, dtype=np.int64), occ)
+    assert len(idx) == n
+    return idx[np.random.default_rng(seed).permutation(n)]
