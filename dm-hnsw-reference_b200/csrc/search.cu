@@ -101,7 +101,11 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, SHN_MIN_BLOCKS) search_ke
     uint32_t c_hot = 0, c_local = 0;
     const uint32_t l0_before = c_vl0;
     beam_search<IP, NCHUNK>(g, s_q, 0, ef, qd, qi, qsize, s_rows, s_dist, vis, c_dist, c_vl0, c_l0, c_hot, c_local, lane);
+#ifdef SHN_COUNT_PREDICTIONS
+    t_hot += c_hot; t_local += c_local;
+#else
     if (g.world > 1) { t_hot += c_hot; t_local += c_local; t_remote += (c_vl0 - l0_before) - c_hot - c_local; }
+#endif
 
     // trim to k (:296-298); the reference reports ids in heap-array order, here ascending by distance
     for (uint32_t j = lane; j < p.k; j += 32) {

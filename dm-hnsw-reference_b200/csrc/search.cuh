@@ -24,7 +24,16 @@ constexpr uint32_t kFull = 0xFFFFFFFFu;
 constexpr uint32_t kExpanded = 0x80000000u;  // flag bit in a queue entry's row id
 constexpr int kMaxList = 64;                  // 2m <= 64
 
+#ifdef SHN_ROW_NO_L1
+// rows are read once per query: keep them out of L1 so that the adjacency lists and the pointer tables stay there
+__device__ __forceinline__ float4 ldg_f4(const float4* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+#else
 __device__ __forceinline__ float4 ldg_f4(const float4* p) { return __ldg(p); }
+#endif
 
 // ---------------------------------------------------------------------------------------------------------------
 // Distances, in the reference's summation order (bit-identical results; see oracle/hnsw_oracle.c for how the
@@ -383,6 +392,22 @@ __device__ __forceinline__ bool visited_test_and_set(VisitedSet& v, uint32_t id,
   return is_new;
 }
 
+// Read-only membership test against the shared table only (keys that spilled to the HBM table are reported as absent):
+// good enough to decide whether a row is worth prefetching.
+__device__ __forceinline__ bool visited_probably(const VisitedSet& v, uint32_t id) {
+  const uint32_t nbuckets = v.cap >> 2;
+  uint32_t b = hash_row(id) & (nbuckets - 1);
+  for (int probe = 0; probe < 4; ++probe) {
+    const uint4 k = reinterpret_cast<const uint4*>(v.tab)[b];
+    if (k.x == id || k.y == id || k.z == id || k.w == id) return true;
+    if (k.w == kInvalid) return false;
+    b = (b + 1) & (nbuckets - 1);
+  }
+  return false;
+}
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 // ---------------------------------------------------------------------------------------------------------------
 // ef-bounded best-first search on one level (HNSW::search_level, hnsw.hh:407-476).  On entry the queue holds the
 // seed entries (unexpanded) and the visited set holds their rows.  Level 0 reads the 2m-wide lists, upper levels the
@@ -400,6 +425,7 @@ __device__ __forceinline__ void beam_search(const DeviceGraph& g, const float* s
   // of it, the next iteration starts with its list already in registers (one dependent HBM round trip per
   // expansion instead of two).  Purely a load-scheduling device: what is expanded, and in which order, is unchanged.
   uint32_t pre_row = kInvalid, pre0 = kInvalid, pre1 = kInvalid;
+  uint32_t c_lists_pred = 0, c_lists_hit = 0;
   for (;;) {
     // next_candidates.pop(): the closest entry not yet expanded
     uint32_t pos = kInvalid;
@@ -418,7 +444,9 @@ __device__ __forceinline__ void beam_search(const DeviceGraph& g, const float* s
 
     // read_neighborlist (:437): from the registers filled during the previous expansion, or from HBM
     uint32_t nb0, nb1 = kInvalid;
+    if (pre_row != kInvalid) ++c_lists_pred;  // diagnostic: a prediction existed
     if (cand == pre_row) {
+      ++c_lists_hit;
       nb0 = pre0; nb1 = pre1;
     } else {
       const uint32_t* list = level == 0 ? l0_row(g, cand)
@@ -476,12 +504,37 @@ __device__ __forceinline__ void beam_search(const DeviceGraph& g, const float* s
         c_local += __popc(__ballot_sync(kFull, mine));
       }
     }
+#ifndef SHN_ROW_PREFETCH
     eval_rows<IP, NCHUNK>(g, s_q, s_rows, cnt, s_dist, lane);
+#else
+    // EXPERIMENT, off by default (measured slower on B200: +25 % DRAM traffic, L2 hit rate 5 % -> 39 %, but 37 % more time
+    // at ef = 64 — the extra traffic lengthens the demand-load latency more than the L2 hits shorten it).
+    // First wave of rows, then — the list of the predicted next candidate has arrived by now — pull that candidate's
+    // unvisited rows into L2 while the remaining waves and the merge run; two times out of three (ef = 64; more at
+    // larger ef) the prediction holds and the next expansion reads its rows from L2 instead of HBM.
+    const uint32_t first = min(cnt, 4u * SHN_PASSES);
+    eval_rows<IP, NCHUNK>(g, s_q, s_rows, first, s_dist, lane);
+    if (level == 0 && pre_row != kInvalid) {
+      const uint32_t lines = (g.row_f4 + 7) >> 3;
+      if (pre0 != kInvalid && pre0 < g.hot && !visited_probably(vis, pre0)) {
+        const char* rp = reinterpret_cast<const char*>(g.vec + static_cast<size_t>(pre0) * g.row_f4);
+        for (uint32_t l = 0; l < lines; ++l) prefetch_l2(rp + 128 * l);
+      }
+      if (width > 32 && pre1 != kInvalid && pre1 < g.hot && !visited_probably(vis, pre1)) {
+        const char* rp = reinterpret_cast<const char*>(g.vec + static_cast<size_t>(pre1) * g.row_f4);
+        for (uint32_t l = 0; l < lines; ++l) prefetch_l2(rp + 128 * l);
+      }
+    }
+    if (cnt > first) eval_rows<IP, NCHUNK>(g, s_q, s_rows + first, cnt - first, s_dist + first, lane);
+#endif
 
     // admission against the running farthest distance (:456-465, heap.hh:34-41), all neighbours in one merge
     const uint32_t at = queue_merge(qd, qi, qsize, ef, s_rows, s_dist, cnt, lane);
     if (at < lb) lb = at;
   }
+#ifdef SHN_COUNT_PREDICTIONS
+  c_hot = c_lists_pred; c_local = c_lists_hit;  // diagnostic build only: reported as rows_hot / rows_local
+#endif
 }
 
 // One step of search_for_one (hnsw.hh:342-391) on `level`: scan the whole list of `cur`, move to the list minimum if
