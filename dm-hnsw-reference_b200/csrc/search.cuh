@@ -24,7 +24,7 @@ constexpr uint32_t kFull = 0xFFFFFFFFu;
 constexpr uint32_t kExpanded = 0x80000000u;  // flag bit in a queue entry's row id
 constexpr int kMaxList = 64;                  // 2m <= 64
 
-#ifdef SHN_ROW_NO_L1
+#ifndef SHN_ROW_L1
 // rows are read once per query: keep them out of L1 so that the adjacency lists and the pointer tables stay there
 __device__ __forceinline__ float4 ldg_f4(const float4* p) {
   float4 v;
@@ -420,12 +420,14 @@ __device__ __forceinline__ void beam_search(const DeviceGraph& g, const float* s
                                             uint32_t& c_local, int lane) {
   const uint32_t width = level == 0 ? g.m0 : g.m;
   uint32_t lb = 0;  // every entry below lb is expanded
-  // The list of the entry most likely to be expanded NEXT (the closest unexpanded one after the current candidate)
-  // is loaded while the current candidate's rows are in flight; if the merge does not put a closer entry in front
-  // of it, the next iteration starts with its list already in registers (one dependent HBM round trip per
-  // expansion instead of two).  Purely a load-scheduling device: what is expanded, and in which order, is unchanged.
+  // Optional (-DSHN_LIST_PREFETCH, off: no measurable gain on B200): the list of the entry most likely to be expanded
+  // NEXT (the closest unexpanded one after the current candidate; right 65 % of the time at ef = 64, 80 % at 256) is
+  // loaded while the current candidate's rows are in flight.  Purely a load-scheduling device: what is expanded, and in
+  // which order, is unchanged.
   uint32_t pre_row = kInvalid, pre0 = kInvalid, pre1 = kInvalid;
+#ifdef SHN_COUNT_PREDICTIONS
   uint32_t c_lists_pred = 0, c_lists_hit = 0;
+#endif
   for (;;) {
     // next_candidates.pop(): the closest entry not yet expanded
     uint32_t pos = kInvalid;
@@ -444,9 +446,11 @@ __device__ __forceinline__ void beam_search(const DeviceGraph& g, const float* s
 
     // read_neighborlist (:437): from the registers filled during the previous expansion, or from HBM
     uint32_t nb0, nb1 = kInvalid;
+#ifdef SHN_COUNT_PREDICTIONS
     if (pre_row != kInvalid) ++c_lists_pred;  // diagnostic: a prediction existed
+    if (cand == pre_row) ++c_lists_hit;
+#endif
     if (cand == pre_row) {
-      ++c_lists_hit;
       nb0 = pre0; nb1 = pre1;
     } else {
       const uint32_t* list = level == 0 ? l0_row(g, cand)
@@ -454,7 +458,7 @@ __device__ __forceinline__ void beam_search(const DeviceGraph& g, const float* s
       nb0 = static_cast<uint32_t>(lane) < width ? __ldg(list + lane) : kInvalid;
       if (width > 32) nb1 = static_cast<uint32_t>(lane) + 32 < width ? __ldg(list + lane + 32) : kInvalid;
     }
-#ifndef SHN_NO_LIST_PREFETCH
+#ifdef SHN_LIST_PREFETCH
     {
       uint32_t pos2 = kInvalid;
       for (uint32_t b = lb & ~31u; b < qsize; b += 32) {
