@@ -146,3 +146,25 @@ def test_store_round_trip(pkg, tmp_path):
     with pkg.Index.load(paths, case["dim"], case["m"]) as ix2:
         again = ix2.search(case["queries"], 10, 64)
     assert (again[0] == ref[0]).all()
+
+
+@pytest.mark.parametrize("m,dim,ip,n", [(32, 64, False, 6000), (24, 48, True, 5000), (16, 128, False, 20000)])
+def test_live_parity_against_reference_built_index(pkg, m, dim, ip, n):
+    """Fresh index built by the reference's own insert path on this box (not a fixture), M up to the reference's default
+    32 (level-0 lists of 64: two list loads per expansion), several ef: GPU vs the pinned oracle, bit for bit."""
+    import shine_ref
+    import datagen
+    if not shine_ref.available():
+        pytest.skip("oracle/_ref not built")
+    base, queries = datagen.base_and_queries(n, 400, dim, normalize=ip)
+    dumps, _, _ = shine_ref.build(base[::-1].copy(), m=m, efc=100, ip=ip, threads=4, seed=99)
+    oracle = hnsw_oracle.Index(dumps, dim, m)
+    with pkg.Index.from_dumps(dumps, dim, m, ip=ip) as ix:
+        for k, ef in ((10, 16), (10, 100), (25, 300)):
+            ids, dists, st = ix.search(queries, k, ef)
+            oi, od, _, ct = oracle.knn(queries, k, ef, ip=ip, counters=True, track_ties=True, threads=4)
+            n_clean = compare(ids, dists, oi, od, ct["tie"])
+            assert n_clean >= 0.9 * len(ids)
+            if (ct["tie"] == 0).all():
+                assert st["distcomps"] == int(ct["distcomps"].sum())
+                assert st["lists_l0"] == int(ct["lists_l0"].sum()) and st["lists_upper"] == int(ct["lists_upper"].sum())
