@@ -2,6 +2,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -854,8 +855,14 @@ int shn_bruteforce_topk_device(const float* d_base, uint64_t n, const float* d_q
   int sms = 0;
   int rc = select_device(gpu_id, &sms);
   if (rc != SHN_OK) return rc;
-  cudaError_t e = bruteforce_launch(d_base, n, d_queries, static_cast<uint32_t>(nq), dim, metric == SHN_IP, k, d_out_ids,
-                                    d_out_dists, sms, static_cast<cudaStream_t>(stream));
+  // SHN_BRUTEFORCE=simt forces the fp32-pipe kernel, =tc the tensor-core one; default: tensor cores when the shape allows
+  const char* mode = std::getenv("SHN_BRUTEFORCE");
+  const bool want_tc = !(mode && std::strcmp(mode, "simt") == 0) && bruteforce_tc_supported(dim, k);
+  if (mode && std::strcmp(mode, "tc") == 0 && !want_tc) return fail(SHN_ERR_ARG, "tensor-core brute force needs dim %% 64 == 0 and k <= 32");
+  cudaError_t e = want_tc ? bruteforce_tc_launch(d_base, n, d_queries, static_cast<uint32_t>(nq), dim, metric == SHN_IP, k, d_out_ids,
+                                                 d_out_dists, sms, static_cast<cudaStream_t>(stream))
+                          : bruteforce_launch(d_base, n, d_queries, static_cast<uint32_t>(nq), dim, metric == SHN_IP, k, d_out_ids,
+                                              d_out_dists, sms, static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return fail(SHN_ERR_CUDA, "bruteforce: %s", cudaGetErrorString(e));
   return SHN_OK;
 }

@@ -46,6 +46,11 @@ cudaError_t search_launch(const DeviceGraph& g, const SearchConfig& cfg, const f
 cudaError_t bruteforce_launch(const float* d_base, uint64_t n, const float* d_queries, uint32_t nq, uint32_t dim, bool ip,
                               uint32_t k, uint32_t* d_ids, float* d_dists, int num_sms, cudaStream_t stream);
 
+// Tensor-core variant (bruteforce_tc.cu): tcgen05 candidate generation (bf16 split operands) + exact fp32 re-rank.
+bool bruteforce_tc_supported(uint32_t dim, uint32_t k);
+cudaError_t bruteforce_tc_launch(const float* d_base, uint64_t n, const float* d_queries, uint32_t nq, uint32_t dim, bool ip,
+                                 uint32_t k, uint32_t* d_ids, float* d_dists, int num_sms, cudaStream_t stream);
+
 // ---- row layout (layout.cu): natural order [n][dim] <-> stored order [n][row_f4*4] (graph.h row_pos), both on device
 cudaError_t rows_to_layout(const float* d_src, float* d_dst, uint64_t n, uint32_t dim, uint32_t row_f4, cudaStream_t stream);
 cudaError_t rows_from_layout(const float* d_src, float* d_dst, uint64_t n, uint32_t dim, uint32_t row_f4, cudaStream_t stream);

@@ -41,3 +41,25 @@ def test_recall_of_the_index_against_gpu_ground_truth(pkg):
     with pkg.Index.build(base, 16, 200) as ix:
         ids, _, _ = ix.search(queries, 10, 64)
     assert datagen.recall(ids, gt) > 0.98
+
+
+@pytest.mark.parametrize("n,nq,dim,k,ip", [(1000, 5, 64, 10, False), (70000, 300, 128, 10, False), (33333, 129, 192, 32, True),
+                                           (5000, 64, 960, 10, False), (300000, 1000, 128, 10, False)])
+def test_tensor_core_path_is_exact(pkg, monkeypatch, n, nq, dim, k, ip):
+    """tcgen05 candidate generation (split-bf16, 3 products) + fp32 re-rank returns what the fp32-pipe kernel returns:
+    same ids, same distance bits (both rank with the same arithmetic; the tensor cores only pick candidates)."""
+    base, queries = datagen.base_and_queries(n, nq, dim, normalize=ip)
+    monkeypatch.setenv("SHN_BRUTEFORCE", "simt")
+    ids_s, d_s = pkg.bruteforce_topk(base, queries, k, ip=ip)
+    monkeypatch.setenv("SHN_BRUTEFORCE", "tc")
+    ids_t, d_t = pkg.bruteforce_topk(base, queries, k, ip=ip)
+    same = (ids_s == ids_t).all(axis=1)
+    assert same.mean() == 1.0, f"{(~same).sum()} of {nq} queries differ"
+    assert (d_s.view(np.uint32) == d_t.view(np.uint32)).all()
+
+
+def test_tensor_core_path_rejects_unsupported_shapes(pkg, monkeypatch):
+    monkeypatch.setenv("SHN_BRUTEFORCE", "tc")
+    base, queries = datagen.base_and_queries(100, 4, 40)
+    with pytest.raises(pkg.ShnError):
+        pkg.bruteforce_topk(base, queries, 5)
