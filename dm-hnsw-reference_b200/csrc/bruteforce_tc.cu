@@ -281,17 +281,30 @@ __global__ void rerank_kernel(const float* __restrict__ base, const float* __res
   __syncwarp();
   const float* qv = queries + static_cast<size_t>(q) * dim;
   const uint32_t total = lists * CAND;
+  // per warp: a 32 x 32 transpose tile so that the 32 candidate rows are read with coalesced 128-byte loads while
+  // every lane still sums ITS candidate in element order
+  float* tile = reinterpret_cast<float*>(sm) + static_cast<size_t>(blockDim.x >> 5) * 2 * k + static_cast<size_t>(warp) * (32 * 33 + 32);
+  float* qchunk = tile + 32 * 33;
   for (uint32_t c0 = 0; c0 < total; c0 += 32) {
     const uint32_t c = c0 + lane;
     uint32_t id = kInvalid;
     if (c < total) id = part_i[(static_cast<size_t>(c / CAND) * nq + q) * CAND + c % CAND];
-    float d = FLT_MAX;
-    if (id != kInvalid) {
-      const float* x = base + static_cast<size_t>(id) * dim;
-      float acc = 0.f;
-      if (ip) { for (uint32_t e = 0; e < dim; ++e) acc = __fmaf_rn(qv[e], x[e], acc); d = __fsub_rn(1.0f, acc); }
-      else { for (uint32_t e = 0; e < dim; ++e) { const float t = __fsub_rn(qv[e], x[e]); acc = __fmaf_rn(t, t, acc); } d = acc; }
+    float acc = 0.f;
+    for (uint32_t e0 = 0; e0 < dim; e0 += 32) {
+      const uint32_t e = e0 + lane;
+      qchunk[lane] = e < dim ? qv[e] : 0.f;
+#pragma unroll 4
+      for (int j = 0; j < 32; ++j) {
+        const uint32_t idj = __shfl_sync(0xFFFFFFFFu, id, j);
+        tile[j * 33 + lane] = (idj != kInvalid && e < dim) ? base[static_cast<size_t>(idj) * dim + e] : 0.f;
+      }
+      __syncwarp();
+      const uint32_t lim = min(32u, dim - e0);
+      if (ip) { for (uint32_t j = 0; j < lim; ++j) acc = __fmaf_rn(qchunk[j], tile[lane * 33 + j], acc); }
+      else { for (uint32_t j = 0; j < lim; ++j) { const float t = __fsub_rn(qchunk[j], tile[lane * 33 + j]); acc = __fmaf_rn(t, t, acc); } }
+      __syncwarp();
     }
+    const float d = id == kInvalid ? FLT_MAX : (ip ? __fsub_rn(1.0f, acc) : acc);
     uint32_t mask = __ballot_sync(0xFFFFFFFFu, id != kInvalid);
     while (mask) {
       const int src = __ffs(mask) - 1;
@@ -364,8 +377,9 @@ cudaError_t bruteforce_tc_launch(const float* d_base, uint64_t n, const float* d
   const uint64_t slab_max = 4ull << 20;  // rows converted to bf16 hi/lo at a time
   const uint32_t qtiles = (nq + BM - 1) / BM;
   const uint32_t n_slabs = static_cast<uint32_t>((n + slab_max - 1) / slab_max);
-  uint32_t slices = std::max<uint32_t>(1, (static_cast<uint32_t>(num_sms) + qtiles - 1) / qtiles);
-  slices = std::min<uint32_t>(slices, 64);
+  // One CTA per SM (199 KB of shared memory).  Slices cost epilogue time (every slice re-warms its candidate lists), so
+  // take as many as fit in ONE wave and no more (measured: 13 slices at 79 query tiles were 2x slower than 1-2).
+  const uint32_t slices = std::max<uint32_t>(1, std::min<uint32_t>(64, static_cast<uint32_t>(num_sms) / qtiles));
   const uint32_t lists = n_slabs * slices;
 
   __nv_bfloat16 *qh = nullptr, *ql = nullptr, *bh = nullptr, *bl = nullptr;
@@ -403,7 +417,7 @@ cudaError_t bruteforce_tc_launch(const float* d_base, uint64_t n, const float* d
   }
   if (e == cudaSuccess) {
     const int warps = 4;
-    rerank_kernel<<<(nq + warps - 1) / warps, warps * 32, warps * 2 * k * sizeof(float), stream>>>(d_base, d_queries, nq, dim, ip ? 1 : 0,
+    rerank_kernel<<<(nq + warps - 1) / warps, warps * 32, warps * (2 * k + 32 * 33 + 32) * sizeof(float), stream>>>(d_base, d_queries, nq, dim, ip ? 1 : 0,
                                                                                                    part_i, lists, k, d_ids, d_dists);
     e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
