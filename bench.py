@@ -345,17 +345,29 @@ def main():
             return ix.search_device(q.data_ptr(), nq, K, ef, ids.data_ptr(), dists.data_ptr(), stream=stream, want_stats=False)
         # route every query to the GPU of its nearest centroid, search there, bring the results home
         torch.cuda.current_stream().synchronize()
+        t0 = time.perf_counter()
         dest = pkg.route_queries(centroids, q.data_ptr(), nq, ip=wl["ip"], slack=0.25, gpu=local_rank)
+        t1 = time.perf_counter()
         ex = par.RoutedExchange(dest, world, dist, dev)
         mine = ex.forward(q)
         m = mine.shape[0]
-        r_ids = torch.empty((m, K), dtype=torch.int32, device=dev)
-        r_d = torch.empty((m, K), dtype=torch.float32, device=dev)
-        st_r = ix.search_device(mine.data_ptr(), m, K, ef, r_ids.data_ptr(), r_d.data_ptr(), stream=stream)
+        r_both = torch.empty((m, 2 * K), dtype=torch.int32, device=dev)   # ids | distance bits: one exchange back
+        torch.cuda.current_stream().synchronize()
+        t2 = time.perf_counter()
+        tmp_i = torch.empty((m, K), dtype=torch.int32, device=dev)
+        tmp_d = torch.empty((m, K), dtype=torch.float32, device=dev)
+        st_r = ix.search_device(mine.data_ptr(), m, K, ef, tmp_i.data_ptr(), tmp_d.data_ptr(), stream=stream)
+        t3 = time.perf_counter()
         route_stats["remote"] += st_r["rows_remote"]
         route_stats["total"] += st_r["rows_hot"] + st_r["rows_local"] + st_r["rows_remote"]
-        ids.copy_(ex.backward(r_ids))
-        dists.copy_(ex.backward(r_d))
+        r_both[:, :K] = tmp_i
+        r_both[:, K:] = tmp_d.view(torch.int32)
+        back = ex.backward(r_both)
+        ids.copy_(back[:, :K])
+        dists.copy_(back[:, K:].view(torch.float32))
+        torch.cuda.current_stream().synchronize()
+        t4 = time.perf_counter()
+        route_stats["t"] = [round(1e3 * x, 1) for x in (t1 - t0, t2 - t1, t3 - t2, t4 - t3)]
         return st_r
 
     def gather():  # per-GPU top-k lists -> every rank, global query order; one all-gather
@@ -401,7 +413,8 @@ def main():
         tot = max(1, st["rows_hot"] + st["rows_local"] + st["rows_remote"])
         remote_bytes = st["rows_remote"] * (4 * wl["dim"]) + (st["rows_remote"] / tot) * st["lists_l0"] * 8 * wl["m"]
         if routed and route_stats["total"]:
-            placement_note = dict(routed_rows_remote=route_stats["remote"] / route_stats["total"])
+            placement_note = dict(routed_rows_remote=route_stats["remote"] / route_stats["total"],
+                                  routed_step_ms=dict(zip(("route", "exchange_out", "search", "exchange_back"), route_stats["t"])))
         else:
             placement_note = {}
         placement = dict(**placement_note, rows_hot=st["rows_hot"] / tot, rows_local=st["rows_local"] / tot, rows_remote=st["rows_remote"] / tot,
