@@ -201,6 +201,8 @@ def main():
     ap.add_argument("--index-mode", default="replica", choices=["replica", "partitioned"],
                     help="N > 1: every GPU holds the whole index (default) or 1/N of it plus a replicated hot set, "
                          "the rest read over NVLink (SURVEY 8e)")
+    ap.add_argument("-m", type=int, default=0, help="override the workload's M (the reference's experiments use 32, scripts/config.py:5-9)")
+    ap.add_argument("--ef-construction", type=int, default=0, help="override the workload's efC (the reference's experiments use 500)")
     ap.add_argument("--zipf", type=float, default=None,
                     help="skew the queries: a pool of 100k distinct queries expanded with Zipf(alpha) popularity exactly as the "
                          "reference's scripts/data/skew.py; the hot-set warm-up then uses queries of the same distribution")
@@ -216,7 +218,13 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    wl = WORKLOADS[args.workload]
+    wl = dict(WORKLOADS[args.workload])
+    if args.m:
+        wl["m"] = args.m
+        wl["label"] = wl["label"].replace("M=16", f"M={args.m}")
+    if args.ef_construction:
+        wl["efc"] = args.ef_construction
+        wl["label"] = wl["label"].replace("efC=200", f"efC={args.ef_construction}")
 
     if args.impl == "reference" and rank != 0:
         return  # rank 0 alone runs the CPU arm
