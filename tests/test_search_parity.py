@@ -164,7 +164,12 @@ def test_live_parity_against_reference_built_index(pkg, m, dim, ip, n):
             ids, dists, st = ix.search(queries, k, ef)
             oi, od, _, ct = oracle.knn(queries, k, ef, ip=ip, counters=True, track_ties=True, threads=4)
             n_clean = compare(ids, dists, oi, od, ct["tie"])
-            assert n_clean >= 0.9 * len(ids)
+            # at large ef two of the few thousand visited nodes often share an fp32 distance (birthday bound), so the
+            # conservative tie flag fires for many queries; the results themselves must still agree almost everywhere
+            assert n_clean >= 0.5 * len(ids)
+            gi, _ = canon(ids, dists)
+            ri, _ = canon(oi, od)
+            assert (gi == ri).all(axis=1).mean() >= 0.99
             if (ct["tie"] == 0).all():
                 assert st["distcomps"] == int(ct["distcomps"].sum())
                 assert st["lists_l0"] == int(ct["lists_l0"].sum()) and st["lists_upper"] == int(ct["lists_upper"].sum())
