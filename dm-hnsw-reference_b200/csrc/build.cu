@@ -272,6 +272,29 @@ __global__ void __launch_bounds__(kBuildWarps * 32, 4) link_kernel(const BuildPa
   if (lane == 0) atomicAdd(p.totals, t_dist);
 }
 
+// Test hook: select_neighbors on one candidate set (rows of the index, ascending by distance), one warp.
+template <bool IP, int NCHUNK>
+__global__ void select_probe_kernel(const DeviceGraph g, const uint32_t* cand_rows, const float* cand_dist, uint32_t n_cand,
+                                    uint32_t m_target, uint32_t* out_rows, uint32_t* out_n, unsigned long long* out_distcomps) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31;
+  float* s_c = reinterpret_cast<float*>(smem_raw);
+  uint32_t* sel_rows = reinterpret_cast<uint32_t*>(s_c + g.row_f4 * 4);
+  float* sel_dist = reinterpret_cast<float*>(sel_rows + kMaxList);
+  float* s_tmp = sel_dist + kMaxList;
+  unsigned long long dc = 0;
+  const uint32_t ns = select_neighbors<IP, NCHUNK>(g, cand_rows, cand_dist, n_cand, m_target, s_c, sel_rows, sel_dist, s_tmp, dc, lane);
+  for (uint32_t j = lane; j < ns; j += 32) out_rows[j] = sel_rows[j];
+  if (lane == 0) { *out_n = ns; *out_distcomps = dc; }
+}
+template <bool IP, int NCHUNK>
+cudaError_t launch_select_probe(const DeviceGraph& g, const uint32_t* cand_rows, const float* cand_dist, uint32_t n_cand,
+                                uint32_t m_target, uint32_t* out_rows, uint32_t* out_n, unsigned long long* out_dc, cudaStream_t s) {
+  const size_t smem = 4ull * (g.row_f4 * 4 + 3 * kMaxList);
+  select_probe_kernel<IP, NCHUNK><<<1, 32, smem, s>>>(g, cand_rows, cand_dist, n_cand, m_target, out_rows, out_n, out_dc);
+  return cudaGetLastError();
+}
+
 template <bool IP, int NCHUNK>
 cudaError_t launch_insert(const BuildParams& p, int grid, size_t smem, cudaStream_t s) {
   insert_search_kernel<IP, NCHUNK><<<grid, kBuildWarps * 32, smem, s>>>(p);
@@ -321,6 +344,13 @@ void draw_levels(uint64_t n, uint32_t m, uint32_t seed, std::vector<uint32_t>& l
     if (l > top) { l = top + 1; top = l; }
     level[i] = l;
   }
+}
+
+cudaError_t select_probe(const DeviceGraph& g, bool ip, const uint32_t* d_cand_rows, const float* d_cand_dist, uint32_t n_cand,
+                         uint32_t m_target, uint32_t* d_out_rows, uint32_t* d_out_n, unsigned long long* d_out_dc, cudaStream_t s) {
+  const uint32_t d_rt = g.dim;
+  const int v = (d_rt == 96 || d_rt == 128 || d_rt == 200 || d_rt == 960) ? static_cast<int>(d_rt) : 0;
+  return DISPATCH(launch_select_probe, ip, v, g, d_cand_rows, d_cand_dist, n_cand, m_target, d_out_rows, d_out_n, d_out_dc, s);
 }
 
 cudaError_t build_graph(BuildJob& job, cudaStream_t stream) {

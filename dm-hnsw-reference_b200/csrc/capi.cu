@@ -297,6 +297,7 @@ int shn_index_load_mem(shn_index** out, const void* const* dumps, const uint64_t
   HostGraph g;
   std::string err;
   if (!parse_dumps(dumps, sizes, n_parts, dim, m, g, err)) return fail(SHN_ERR_IO, "%s", err.c_str());
+  if (g.n >= (1u << 31)) return fail(SHN_ERR_ARG, "more than 2^31 - 1 nodes (the top bit of a row id marks expanded queue entries)");
   shn_index* ix = nullptr;
   int rc = new_handle(&ix, gpu_id, metric);
   if (rc != SHN_OK) return rc;
@@ -409,6 +410,14 @@ int shn_index_build(shn_index** out, const float* base, const uint32_t* ids, uin
   rc = shn_index_build_device(out, d_base, d_ids, n, dim, m, ef_construction, metric, seed, gpu_id);
   cudaFree(d_base); cudaFree(d_ids);
   return rc;
+}
+
+int shn_draw_levels(uint64_t n, uint32_t m, uint32_t seed, uint32_t* levels) {
+  if (!levels || m < 2) return fail(SHN_ERR_ARG, "need an output buffer and m >= 2");
+  std::vector<uint32_t> l;
+  draw_levels(n, m, seed, l);
+  std::memcpy(levels, l.data(), n * sizeof(uint32_t));
+  return SHN_OK;
 }
 
 int shn_set_build_option(const char* key, int64_t value) {
@@ -850,6 +859,33 @@ int shn_index_partition_attach(shn_index* ix, int peer, const int* fds, const ui
   CU(cudaMemcpy(ix->d_part_vec + peer, &vp, sizeof(void*), cudaMemcpyHostToDevice));
   CU(cudaMemcpy(ix->d_part_l0 + peer, &lp, sizeof(void*), cudaMemcpyHostToDevice));
   ++ix->attached;
+  return SHN_OK;
+}
+
+// Test hook (not in include/shn.h): the builder's select_neighbors (= HNSW::select_heuristic, hnsw.hh:482-522) on one
+// candidate set: rows of the index with their distances to some query, ascending.  Host buffers.
+int shn_debug_select_neighbors(shn_index* ix, const uint32_t* cand_rows, const float* cand_dist, uint32_t n_cand, uint32_t m_target,
+                               uint32_t* out_rows, uint32_t* out_n, uint64_t* out_distcomps) {
+  if (!ix || !cand_rows || !cand_dist || !out_rows || !out_n || n_cand == 0 || n_cand > 4096 || m_target == 0 || m_target > 64)
+    return fail(SHN_ERR_ARG, "bad arguments");
+  if (ix->world > 1) return fail(SHN_ERR_STATE, "not on a partitioned handle");
+  CU(cudaSetDevice(ix->gpu));
+  uint32_t *d_rows = nullptr, *d_out = nullptr, *d_n = nullptr;
+  float* d_dist = nullptr;
+  unsigned long long* d_dc = nullptr;
+  CU(cudaMalloc(&d_rows, n_cand * 4)); CU(cudaMalloc(&d_dist, n_cand * 4)); CU(cudaMalloc(&d_out, 64 * 4));
+  CU(cudaMalloc(&d_n, 4)); CU(cudaMalloc(&d_dc, 8));
+  CU(cudaMemcpy(d_rows, cand_rows, n_cand * 4, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(d_dist, cand_dist, n_cand * 4, cudaMemcpyHostToDevice));
+  cudaError_t e = select_probe(ix->view(), ix->metric == SHN_IP, d_rows, d_dist, n_cand, m_target, d_out, d_n, d_dc, ix->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ix->stream);
+  unsigned long long dc = 0;
+  if (e == cudaSuccess) e = cudaMemcpy(out_n, d_n, 4, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cudaMemcpy(out_rows, d_out, 64 * 4, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cudaMemcpy(&dc, d_dc, 8, cudaMemcpyDeviceToHost);
+  cudaFree(d_rows); cudaFree(d_dist); cudaFree(d_out); cudaFree(d_n); cudaFree(d_dc);
+  if (e != cudaSuccess) return fail(SHN_ERR_CUDA, "select probe: %s", cudaGetErrorString(e));
+  if (out_distcomps) *out_distcomps = dc;
   return SHN_OK;
 }
 

@@ -97,5 +97,8 @@ struct BuildJob {
 
 void draw_levels(uint64_t n, uint32_t m, uint32_t seed, std::vector<uint32_t>& level);
 cudaError_t build_graph(BuildJob& job, cudaStream_t stream);
+// test hook: the neighbour-selection heuristic of the builder on one candidate set (<= 4096 rows of the index, ascending)
+cudaError_t select_probe(const DeviceGraph& g, bool ip, const uint32_t* d_cand_rows, const float* d_cand_dist, uint32_t n_cand,
+                         uint32_t m_target, uint32_t* d_out_rows, uint32_t* d_out_n, unsigned long long* d_out_dc, cudaStream_t s);
 
 }  // namespace shn

@@ -199,37 +199,6 @@ __device__ SHN_EVAL_ATTR void eval_rows(const DeviceGraph& g, const float* s_q, 
 // it on an exact distance tie (hnsw.hh:424 breaks on strictly greater) — see DESIGN.md "ties".
 // ---------------------------------------------------------------------------------------------------------------
 
-// Insert (d, id) keeping ascending order, stable (after equal distances), dropping the last entry when full.
-// Returns the insert position, or 0xFFFFFFFF if the entry fell off the end.
-__device__ __forceinline__ uint32_t queue_insert(float* qd, uint32_t* qi, uint32_t& qsize, uint32_t ef, float d,
-                                                 uint32_t id, int lane) {
-  uint32_t pos = 0;
-  for (uint32_t b = 0; b < qsize; b += 32) {
-    const uint32_t j = b + lane;
-    const bool le = (j < qsize) && (qd[j] <= d);
-    pos += __popc(__ballot_sync(kFull, le));
-  }
-  const uint32_t nsize = qsize < ef ? qsize + 1 : ef;
-  if (pos >= nsize) return kInvalid;
-  int hi = static_cast<int>(nsize) - 1;  // entries [pos, hi) move up by one, highest block first
-  while (hi > static_cast<int>(pos)) {
-    const int lo = max(static_cast<int>(pos), hi - 32);
-    const int j = lo + lane;
-    const bool act = j < hi;
-    float td = 0.f;
-    uint32_t ti = 0;
-    if (act) { td = qd[j]; ti = qi[j]; }
-    __syncwarp();
-    if (act) { qd[j + 1] = td; qi[j + 1] = ti; }
-    __syncwarp();
-    hi = lo;
-  }
-  if (lane == 0) { qd[pos] = d; qi[pos] = id; }
-  __syncwarp();
-  qsize = nsize;
-  return pos;
-}
-
 // Admit the candidates (s_rows[i], s_dist[i]), i < cnt <= 64, given in stored list order, in ONE merge.
 // Equivalent to the reference's one-by-one admission (hnsw.hh:456-465) whenever no two distances are equal: the
 // running farthest distance only shrinks, so what survives is exactly the ef smallest of old and new entries;

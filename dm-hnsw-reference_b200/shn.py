@@ -79,6 +79,7 @@ def lib():
         L.shn_route_queries.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_int, C.c_void_p, C.c_uint64, C.c_double, C.c_void_p, C.c_int]
         L.shn_index_partition_export.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.shn_index_partition_attach.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.shn_draw_levels.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p]
         L.shn_set_build_option.argtypes = [C.c_char_p, C.c_int64]
         L.shn_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int64]
         L.shn_search.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p,
@@ -292,3 +293,10 @@ def route_queries(centroids, d_queries, nq, ip=False, slack=0.25, gpu=0):
     _check(lib().shn_route_queries(c.ctypes.data, c.shape[0], c.shape[1], IP if ip else L2, d_queries, nq, slack,
                                    dest.ctypes.data, gpu))
     return dest
+
+
+def draw_levels(n, m, seed=1234):
+    """Host-only: node levels as the GPU builder (and a single-coroutine reference build) draws them."""
+    out = np.empty(n, np.uint32)
+    _check(lib().shn_draw_levels(n, m, seed, out.ctypes.data))
+    return out

@@ -78,6 +78,10 @@ int shn_index_build(shn_index** out, const float* base, const uint32_t* ids, uin
 /* Same with base already in device memory on gpu_id (row stride = dim floats). */
 int shn_index_build_device(shn_index** out, const float* d_base, const uint32_t* d_ids, uint64_t n, uint32_t dim,
                            uint32_t m, uint32_t ef_construction, shn_metric metric, uint32_t seed, int gpu_id);
+/* Host-only: the level of every node as shn_index_build* will draw it — HNSW::insert's recipe (hnsw.hh:48,563-564:
+ * floor(-ln(U)/ln(m)), U from uniform_real_distribution<double> over mt19937(seed)), the first node at level 0 (:61),
+ * never more than one above the current top (:106).  Identical to a single-coroutine build of the reference. */
+int shn_draw_levels(uint64_t n, uint32_t m, uint32_t seed, uint32_t* levels);
 /* Construction knobs, process-wide, read when shn_index_build* starts: "batch_max" (nodes inserted per step, default
  * 16384) and "batch_div" (a step inserts at most 1/batch_div of the current graph, default 32); 0 = default. */
 int shn_set_build_option(const char* key, int64_t value);

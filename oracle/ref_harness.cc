@@ -28,7 +28,11 @@
 
 #include "cache/cache.hh"
 #include "compute_thread.hh"
+// HNSW<D>::select_heuristic (hnsw.hh:482-522) is a private static member; the harness reaches it by relaxing access for
+// this one include — the reference source itself stays untouched.
+#define private public
 #include "hnsw/hnsw.hh"
+#undef private
 #include "hnsw/scheduler.hh"
 #include "io/database.hh"
 
@@ -277,6 +281,40 @@ int search_impl(const uint8_t* const* dumps, const uint64_t* sizes, u32 num_mn, 
   return 0;
 }
 
+// HNSW<D>::select_heuristic (hnsw.hh:482-522) on a candidate set given as (uid, distance to the query, components):
+// `selected` receives the candidate indices left in top_candidates, in heap-array order after make_heap (:521).
+// Returns the number selected; *distcomps the reference's counter.
+template <class D>
+uint32_t select_impl(const uint32_t* uids, const float* dists, const float* vectors, uint32_t c, uint32_t dim, uint32_t m,
+                            uint32_t* selected, uint64_t* distcomps) {
+  hnsw::HNSW<D> index{m, 200, 1, 1, 1234, dim, false};
+  vec<byte_t*> none;
+  byte_t* fake_mn = static_cast<byte_t*>(std::calloc(64, 1));
+  none.push_back(fake_mn);
+  uint32_t n_sel = 0;
+  {
+    Pool pool(1, 1, none, 0, false);
+    auto& thread = pool.threads[0];
+    MaxHeap heap;
+    std::unordered_map<u32, uint32_t> index_of;
+    for (uint32_t i = 0; i < c; ++i) {
+      byte_t* buf = thread->buffer_allocator.allocate_node(0);  // returned to the freelist by ~Node
+      std::memset(buf, 0, Node::size_until_components());
+      *reinterpret_cast<u32*>(buf + 8) = uids[i];
+      std::memcpy(buf + 16, vectors + static_cast<size_t>(i) * dim, dim * sizeof(float));
+      heap.push({std::make_shared<Node>(buf, RemotePtr{}, thread.get()), dists[i]});
+      index_of[uids[i]] = i;
+    }
+    const uint64_t before = thread->stats.distcomps;
+    hnsw::HNSW<D>::select_heuristic(heap, m, thread);
+    if (distcomps) *distcomps = thread->stats.distcomps - before;
+    for (const auto& e : heap.heap) selected[n_sel++] = index_of.at(e.node->id());
+    heap.clear();
+  }
+  std::free(fake_mn);
+  return n_sel;
+}
+
 }  // namespace
 
 extern "C" {
@@ -315,6 +353,13 @@ int shine_ref_search(const uint8_t* const* dumps, const uint64_t* sizes, uint32_
 float shine_ref_dist(const float* a, const float* b, uint32_t dim, int ip) {
   return ip ? IPDistance::dist(span<const f32>(a, dim), span<const f32>(b, dim), dim)
             : L2Distance::dist(span<const f32>(a, dim), span<const f32>(b, dim), dim);
+}
+
+uint32_t shine_ref_select_heuristic(const uint32_t* uids, const float* dists, const float* vectors, uint32_t c, uint32_t dim,
+                                    uint32_t m, int ip, uint32_t* selected, uint64_t* distcomps) {
+  SilenceStderr hush(true);  // the cache prints its histograms on teardown
+  return ip ? select_impl<IPDistance>(uids, dists, vectors, c, dim, m, selected, distcomps)
+            : select_impl<L2Distance>(uids, dists, vectors, c, dim, m, selected, distcomps);
 }
 
 void shine_ref_free(void* p) { std::free(p); }

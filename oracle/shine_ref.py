@@ -29,6 +29,7 @@ def lib():
         _lib = C.CDLL(LIB_PATH)
         _lib.shine_ref_dist.restype = C.c_float
         _lib.shine_ref_stats_words.restype = C.c_uint32
+        _lib.shine_ref_select_heuristic.restype = C.c_uint32
         assert _lib.shine_ref_stats_words() == len(STAT_FIELDS)
     return _lib
 
@@ -95,3 +96,18 @@ def dist(a, b, ip=False):
     b = np.ascontiguousarray(b, dtype=np.float32)
     return float(lib().shine_ref_dist(a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p),
                                       C.c_uint32(a.size), C.c_int(int(ip))))
+
+
+def select_heuristic(uids, dists, vectors, m, ip=False):
+    """The reference's HNSW<D>::select_heuristic (hnsw.hh:482-522): returns (selected candidate indices in the
+    heap-array order the reference leaves them in, distcomps)."""
+    uids = np.ascontiguousarray(uids, np.uint32)
+    dists = np.ascontiguousarray(dists, np.float32)
+    vectors = np.ascontiguousarray(vectors, np.float32)
+    c, dim = vectors.shape
+    sel = np.empty(max(c, 1), np.uint32)
+    dc = C.c_uint64()
+    n = lib().shine_ref_select_heuristic(uids.ctypes.data_as(C.c_void_p), dists.ctypes.data_as(C.c_void_p),
+                                         vectors.ctypes.data_as(C.c_void_p), C.c_uint32(c), C.c_uint32(dim), C.c_uint32(m),
+                                         C.c_int(int(ip)), sel.ctypes.data_as(C.c_void_p), C.byref(dc))
+    return sel[:n].copy(), dc.value

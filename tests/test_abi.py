@@ -93,3 +93,24 @@ def test_dump_writer_round_trip(pkg, name, parts):
     rb = b.knn(case["queries"], k, ef, ip=case["ip"], counters=True)
     assert (ra[0] == rb[0]).all() and (ra[1].view(np.uint32) == rb[1].view(np.uint32)).all()
     assert (ra[3]["distcomps"] == rb[3]["distcomps"]).all()
+
+
+@pytest.mark.parametrize("name", ["l2_d32_n2000_m16", "ip_d40_n1500_m8", "l2_d20_n300_m4_3mn"])
+def test_level_recipe_matches_the_reference_build(pkg, name):
+    """Host code only: the levels the GPU builder will draw equal the levels in a dump the reference itself built with
+    the same seed and m (fixtures: seed 1234, one thread, four coroutines — the first inserts race for the empty index
+    and are written at level 0, hnsw.hh:56-85, so they are left out of the comparison)."""
+    case = golden_io.load_case(name)
+    ex = hnsw_oracle.Index(case["dumps"], case["dim"], case["m"]).export()
+    ref = ex["level"][np.argsort(ex["uid"])]
+    got = pkg.draw_levels(case["n"], case["m"], seed=1234)
+    assert got[0] == 0 and len(got) == case["n"]
+    assert (got[4:] == ref[4:]).all()
+    assert ref.max() >= 1
+
+
+def test_level_recipe_is_capped_and_seeded(pkg):
+    a = pkg.draw_levels(100000, 2, seed=5)
+    assert (pkg.draw_levels(100000, 2, seed=5) == a).all() and not (pkg.draw_levels(100000, 2, seed=6) == a).all()
+    top = np.maximum.accumulate(a)
+    assert (np.diff(top) <= 1).all()  # never more than one above the current top (hnsw.hh:106)

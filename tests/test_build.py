@@ -104,3 +104,30 @@ def test_build_argument_errors(pkg):
     with pkg.Index.build(base, 4, 10) as ix:  # all rows identical (zeros): ties everywhere, must still terminate
         ids, _, _ = ix.search(base[:2], 5, 10)
         assert (ids != 0xFFFFFFFF).all()
+
+
+@pytest.mark.parametrize("n,dim,m_target,ip,c", [(3000, 32, 16, False, 100), (2000, 128, 32, False, 60), (2000, 40, 8, True, 200),
+                                                 (500, 96, 16, False, 10)])
+def test_gpu_selection_heuristic_matches_the_oracle(pkg, n, dim, m_target, ip, c):
+    """The builder's select_neighbors kernel routine against the pinned restatement of HNSW::select_heuristic
+    (hnsw.hh:482-522) on random candidate sets: same selected nodes."""
+    import ctypes as C
+    lib = pkg.shn.lib()
+    lib.shn_debug_select_neighbors.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p,
+                                               C.c_void_p, C.c_void_p]
+    base, queries = datagen.base_and_queries(n, 8, dim, normalize=ip)
+    rng = np.random.default_rng(n + c)
+    with pkg.Index.build(base, 8, 40, ip=ip) as ix:  # rows of a built index are in insertion order: row r = base[r]
+        for q in queries:
+            rows = rng.choice(n, size=c, replace=False).astype(np.uint32)
+            d = np.array([hnsw_oracle.dist(q, base[r], ip) for r in rows], np.float32)
+            order = np.lexsort((rows, d))
+            rows, d = rows[order], d[order]
+            out = np.zeros(64, np.uint32)
+            cnt = C.c_uint32()
+            dc = C.c_uint64()
+            rc = lib.shn_debug_select_neighbors(ix._h, rows.ctypes.data, d.ctypes.data, c, m_target, out.ctypes.data,
+                                                C.byref(cnt), C.byref(dc))
+            assert rc == 0, lib.shn_last_error()
+            want, _ = hnsw_oracle.select_heuristic(rows, d, base[rows], m_target, ip)
+            assert sorted(out[:cnt.value].tolist()) == sorted(rows[want].tolist())

@@ -108,3 +108,19 @@ def test_reference_cache_does_not_change_results():
     b = shine_ref.search(case["dumps"], 32, 16, case["queries"], 10, 64, cache_ratio_pct=20)
     assert (a[0] == b[0]).all()
     assert b[3]["cache_hits"] > 0
+
+
+@needs_ref
+@pytest.mark.parametrize("c,dim,m,ip", [(40, 24, 8, False), (5, 16, 8, False), (200, 128, 16, False), (64, 40, 32, True),
+                                        (16, 32, 16, False), (33, 96, 32, False)])
+def test_select_heuristic_matches_reference_live(c, dim, m, ip):
+    """The reference's own HNSW<D>::select_heuristic (hnsw.hh:482-522, reached through the harness) vs the restatement:
+    same selected candidates, same distance-computation count."""
+    rng = np.random.default_rng(c * 1000 + dim)
+    vec = rng.standard_normal((c, dim)).astype(np.float32)
+    q = rng.standard_normal(dim).astype(np.float32)
+    d = np.array([shine_ref.dist(q, v, ip) for v in vec], np.float32)
+    uids = rng.permutation(10 * c)[:c].astype(np.uint32)
+    r_sel, r_dc = shine_ref.select_heuristic(uids, d, vec, m, ip)
+    o_sel, o_dc = hnsw_oracle.select_heuristic(uids, d, vec, m, ip)
+    assert sorted(r_sel.tolist()) == sorted(o_sel.tolist()) and r_dc == o_dc
