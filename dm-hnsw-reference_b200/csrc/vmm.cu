@@ -55,11 +55,30 @@ cudaError_t map_block(const Driver& d, VmmBlock& b, int device, const char** why
   CUdeviceptr va = 0;
   if (d.MemAddressReserve(&va, b.size, 0, 0, 0) != CUDA_SUCCESS) { *why = "cuMemAddressReserve"; return cudaErrorMemoryAllocation; }
   if (d.MemMap(va, b.size, 0, b.handle, 0) != CUDA_SUCCESS) { d.MemAddressFree(va, b.size); *why = "cuMemMap"; return cudaErrorMemoryAllocation; }
-  CUmemAccessDesc acc = {};
-  acc.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
-  acc.location.id = device;
-  acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
-  if (d.MemSetAccess(va, b.size, &acc, 1) != CUDA_SUCCESS) {
+  // read/write for the mapping device, and for every other GPU of this process that can reach it over NVLink/PCIe peer
+  // access: handles that live in the SAME process exchange raw pointers (shn_index_partition_attach raw_ptrs), and a
+  // VMM mapping is only visible to the devices named here (cudaDeviceEnablePeerAccess does not cover VMM memory)
+  CUmemAccessDesc acc[16] = {};
+  size_t n_acc = 0;
+  acc[n_acc].location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+  acc[n_acc].location.id = device;
+  acc[n_acc].flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+  ++n_acc;
+  int count = 0;
+  if (!b.imported && cudaGetDeviceCount(&count) == cudaSuccess) {
+    for (int other = 0; other < count && n_acc < 16; ++other) {
+      int can = 0;
+      if (other != device && cudaDeviceCanAccessPeer(&can, other, device) == cudaSuccess && can) {
+        acc[n_acc].location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+        acc[n_acc].location.id = other;
+        acc[n_acc].flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+        ++n_acc;
+      }
+    }
+  }
+  CUresult rs = d.MemSetAccess(va, b.size, acc, n_acc);
+  if (rs != CUDA_SUCCESS && n_acc > 1) rs = d.MemSetAccess(va, b.size, acc, 1);  // peers refused: at least the owner
+  if (rs != CUDA_SUCCESS) {
     d.MemUnmap(va, b.size); d.MemAddressFree(va, b.size);
     *why = "cuMemSetAccess (no peer access between the two GPUs?)";
     return cudaErrorPeerAccessUnsupported;

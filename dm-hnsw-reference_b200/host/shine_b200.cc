@@ -25,6 +25,7 @@
 #include <map>
 #include <memory>
 #include <sstream>
+#include <thread>
 #include <string>
 #include <variant>
 #include <vector>
@@ -55,7 +56,8 @@ struct Config {
   bool disable_thread_pinning = false, store_index = false, load_index = false, use_cache = false, routing = false,
        no_recall = false, ip_dist = false;
   uint32_t cache_ratio = 5, ef_search = 0, ef_construction = 200, k = 0, m = 32;
-  int gpu = 0;  // extension: --gpu <ordinal>
+  int gpu = 0;   // extension: --gpu <ordinal>: first GPU to use
+  int gpus = 1;  // extension: --gpus <n>: spread the index over n GPUs (memory nodes -> HBM partitions, NVLink peer reads)
 };
 
 [[noreturn]] void usage_exit(const char* argv0) {
@@ -83,7 +85,7 @@ Config parse(int argc, char** argv) {
     try {
       if (a == "--help" || a == "-h") {
         std::cerr << "shine_b200: B200-native compute node; options as in the reference (src/common/configuration.hh, "
-                     "rdma-library/library/configuration.cc) plus --gpu <ordinal>" << std::endl;
+                     "rdma-library/library/configuration.cc) plus --gpu <ordinal> and --gpus <n>" << std::endl;
         std::exit(EXIT_FAILURE);
       } else if (a == "--is-server") c.is_server = true;
       else if (a == "--servers") multi(c.servers);
@@ -114,6 +116,7 @@ Config parse(int argc, char** argv) {
       else if (a == "-k" || a == "--k") c.k = static_cast<uint32_t>(std::stoul(val()));
       else if (a == "-m" || a == "--m") c.m = static_cast<uint32_t>(std::stoul(val()));
       else if (a == "--gpu") c.gpu = std::stoi(val());
+      else if (a == "--gpus") c.gpus = std::stoi(val());
       else { std::cerr << "[ERROR]: unrecognised option '" << a << "'" << std::endl; usage_exit(argv[0]); }
     } catch (const std::exception& e) {
       std::cerr << "[ERROR]: the argument for option '" << a << "' is invalid" << std::endl;
@@ -308,50 +311,122 @@ int main(int argc, char** argv) {
   std::vector<const char*> dump_paths;
   for (auto& f : dump_files) dump_paths.push_back(f.c_str());
 
-  shn_index* index = nullptr;
+  if (cfg.gpus < 1 || cfg.gpus > 8) die("--gpus must be in [1, 8]");
+  const int n_gpus = cfg.gpus;
   double build_ms = 0.0;
   shn_stats bstats;
   std::memset(&bstats, 0, sizeof bstats);
-  if (cfg.load_index) {
-    status("load index from " + dump_files.front());
-    SHN(shn_index_load(&index, dump_paths.data(), static_cast<int>(num_servers), base.dim, cfg.m, metric, cfg.gpu));
-  } else {
-    status("build index");
-    const uint32_t seed = cfg.seed == -1 ? static_cast<uint32_t>(std::time(nullptr)) : static_cast<uint32_t>(cfg.seed);
-    const double t0 = now_ms();
-    SHN(shn_index_build(&index, base.f.data(), nullptr, base.n, base.dim, cfg.m, cfg.ef_construction, metric, seed, cfg.gpu));
-    build_ms = now_ms() - t0;
-    SHN(shn_index_build_stats(index, &bstats));
-    status("processed inserts: " + std::to_string(base.n));
-    if (cfg.store_index) {
-      status("store index to " + dump_files.front());
-      std::error_code ec;
-      fs::create_directories(data_path / "dump", ec);
-      SHN(shn_index_store(index, dump_paths.data(), static_cast<int>(num_servers)));
+  uint64_t index_dump_bytes = 0, hbm_bytes = 0;
+  uint32_t index_max_level = 0;
+  std::vector<uint32_t> ids(static_cast<size_t>(std::max(queries.n, warmup.n)) * cfg.k);
+
+  // One full index per GPU (the build is deterministic, so the graphs are identical).  With one GPU it is searched as
+  // it is; with several, every GPU keeps its share (shn_index_partition) and reads the rest from its peers — the
+  // reference's memory nodes become HBM partitions, its compute-node cache the replicated hot set.
+  auto make_full = [&](int gpu, bool first) -> shn_index* {
+    shn_index* full = nullptr;
+    if (cfg.load_index) {
+      if (first) status("load index from " + dump_files.front());
+      SHN(shn_index_load(&full, dump_paths.data(), static_cast<int>(num_servers), base.dim, cfg.m, metric, gpu));
+    } else {
+      if (first) status("build index");
+      const uint32_t seed = cfg.seed == -1 ? static_cast<uint32_t>(std::time(nullptr)) : static_cast<uint32_t>(cfg.seed);
+      const double t0 = now_ms();
+      SHN(shn_index_build(&full, base.f.data(), nullptr, base.n, base.dim, cfg.m, cfg.ef_construction, metric, seed, gpu));
+      if (first) {
+        build_ms = now_ms() - t0;
+        SHN(shn_index_build_stats(full, &bstats));
+        status("processed inserts: " + std::to_string(base.n));
+        if (cfg.store_index) {
+          status("store index to " + dump_files.front());
+          std::error_code ec;
+          fs::create_directories(data_path / "dump", ec);
+          SHN(shn_index_store(full, dump_paths.data(), static_cast<int>(num_servers)));
+        }
+      }
+    }
+    if (shn_index_size(full) != base.n) die("index holds " + std::to_string(shn_index_size(full)) + " nodes but base has " + std::to_string(base.n));
+    if (first) { index_dump_bytes = shn_index_dump_bytes(full); index_max_level = shn_index_max_level(full); }
+    return full;
+  };
+
+  std::vector<shn_index*> handles(n_gpus, nullptr);
+  for (int g = 0; g < n_gpus; ++g) {
+    shn_index* full = make_full(cfg.gpu + g, g == 0);
+    if (n_gpus == 1) {
+      // -------- cache warm-up pass (compute_node.cc:116-131): results are discarded
+      if (cfg.use_cache && warmup.n) {
+        status("run warmup queries");
+        SHN(shn_search(full, warmup.f.data(), warmup.n, cfg.k, cfg.ef_search, ids.data(), nullptr, nullptr));
+      }
+      handles[g] = full;
+    } else {
+      if (cfg.use_cache && warmup.n) {  // the warm-up pass picks the hot set: same queries, so the same set on every GPU
+        if (g == 0) status("run warmup queries");
+        SHN(shn_index_count_visits(full, 1));
+        SHN(shn_search(full, warmup.f.data(), warmup.n, cfg.k, cfg.ef_search, ids.data(), nullptr, nullptr));
+      }
+      SHN(shn_index_partition(&handles[g], full, g, n_gpus, cfg.use_cache ? cfg.cache_ratio : 0, nullptr));
+      shn_index_free(full);
+    }
+    hbm_bytes += shn_index_hbm_bytes(handles[g]);
+  }
+  if (n_gpus > 1) {
+    for (int g = 0; g < n_gpus; ++g) {
+      uint64_t raw[2];
+      SHN(shn_index_partition_export(handles[g], nullptr, nullptr, raw));
+      for (int o = 0; o < n_gpus; ++o) if (o != g) SHN(shn_index_partition_attach(handles[o], g, nullptr, nullptr, raw));
     }
   }
-  if (shn_index_size(index) != base.n) die("index holds " + std::to_string(shn_index_size(index)) + " nodes but base has " + std::to_string(base.n));
-  out["allocated_local_buffer_size"] = shn_index_hbm_bytes(index);
-  out["actual_total_local_buffer_size"] = shn_index_hbm_bytes(index);
+  out["allocated_local_buffer_size"] = hbm_bytes;
+  out["actual_total_local_buffer_size"] = hbm_bytes;
   out["build"]["dist_comps"] = bstats.distcomps;
   out["build"]["rdma_reads_in_bytes"] = uint64_t{0};
   out["build"]["rdma_writes_in_bytes"] = uint64_t{0};
   out["build"]["remote_allocations"] = cfg.load_index ? uint64_t{0} : uint64_t{base.n};
-  out["build"]["index_size"] = cfg.load_index ? uint64_t{0} : shn_index_dump_bytes(index);
-  out["build"]["max_level"] = cfg.load_index ? 0u : shn_index_max_level(index);
+  out["build"]["index_size"] = cfg.load_index ? uint64_t{0} : index_dump_bytes;
+  out["build"]["max_level"] = cfg.load_index ? 0u : index_max_level;
 
-  // -------- cache warm-up pass (compute_node.cc:116-131): results are discarded
-  std::vector<uint32_t> ids(static_cast<size_t>(std::max(queries.n, warmup.n)) * cfg.k);
-  if (cfg.use_cache && warmup.n) {
-    status("run warmup queries");
-    SHN(shn_search(index, warmup.f.data(), warmup.n, cfg.k, cfg.ef_search, ids.data(), nullptr, nullptr));
-  }
-
-  // -------- queries (compute_node.cc:140, 354-386)
+  // -------- queries (compute_node.cc:140, 354-386): GPU g takes the queries with id % gpus == g (io/read_data.hh:58)
   status("run queries");
   shn_stats st;
+  std::memset(&st, 0, sizeof st);
+  std::vector<shn_stats> per_gpu(n_gpus);
   const double q0 = now_ms();
-  SHN(shn_search(index, queries.f.data(), queries.n, cfg.k, cfg.ef_search, ids.data(), nullptr, &st));
+  if (n_gpus == 1) {
+    SHN(shn_search(handles[0], queries.f.data(), queries.n, cfg.k, cfg.ef_search, ids.data(), nullptr, &st));
+    per_gpu[0] = st;
+  } else {
+    std::vector<std::string> errors(n_gpus);
+    std::vector<std::thread> workers;
+    for (int g = 0; g < n_gpus; ++g) {
+      workers.emplace_back([&, g] {
+        std::vector<float> shard;
+        std::vector<uint32_t> slots;
+        for (uint32_t q = g; q < queries.n; q += n_gpus) {
+          slots.push_back(q);
+          shard.insert(shard.end(), queries.f.begin() + static_cast<size_t>(q) * queries.dim, queries.f.begin() + static_cast<size_t>(q + 1) * queries.dim);
+        }
+        std::vector<uint32_t> res(slots.size() * cfg.k);
+        if (shn_search(handles[g], shard.data(), slots.size(), cfg.k, cfg.ef_search, res.data(), nullptr, &per_gpu[g]) != SHN_OK) {
+          errors[g] = shn_last_error();
+          return;
+        }
+        for (size_t i = 0; i < slots.size(); ++i)
+          std::memcpy(ids.data() + static_cast<size_t>(slots[i]) * cfg.k, res.data() + i * cfg.k, cfg.k * sizeof(uint32_t));
+      });
+    }
+    for (auto& w : workers) w.join();
+    for (int g = 0; g < n_gpus; ++g) if (!errors[g].empty()) die("shn_search on GPU " + std::to_string(cfg.gpu + g) + ": " + errors[g]);
+    for (int g = 0; g < n_gpus; ++g) {
+      const shn_stats& p = per_gpu[g];
+      st.distcomps += p.distcomps; st.visited_nodes += p.visited_nodes; st.visited_nodes_l0 += p.visited_nodes_l0;
+      st.visited_neighborlists += p.visited_neighborlists; st.reference_layout_bytes += p.reference_layout_bytes;
+      st.algorithmic_bytes += p.algorithmic_bytes; st.processed += p.processed;
+      st.rows_hot += p.rows_hot; st.rows_local += p.rows_local; st.rows_remote += p.rows_remote;
+      st.kernel_ms = std::max(st.kernel_ms, p.kernel_ms); st.h2d_ms = std::max(st.h2d_ms, p.h2d_ms); st.d2h_ms = std::max(st.d2h_ms, p.d2h_ms);
+    }
+  }
   const double query_ms = now_ms() - q0;
   status("processed queries: " + std::to_string(st.processed));
 
@@ -383,7 +458,7 @@ int main(int argc, char** argv) {
   qj["visited_nodes_l0"] = st.visited_nodes_l0;
   qj["visited_neighborlists"] = st.visited_neighborlists;
   qj["processed"] = st.processed;
-  qj["processed_local"]["c0"] = st.processed;
+  for (int g = 0; g < n_gpus; ++g) qj["processed_local"]["c" + std::to_string(g)] = per_gpu[g].processed;
   qj["queries_per_sec"] = static_cast<uint64_t>(queries.n / (query_ms / 1000.0));
   qj["compute_recall"] = compute_recall;
   // extension keys (not in the reference): device-side view of the same run
@@ -391,10 +466,14 @@ int main(int argc, char** argv) {
   qj["gpu_h2d_ms"] = st.h2d_ms;
   qj["gpu_d2h_ms"] = st.d2h_ms;
   qj["algorithmic_bytes"] = st.algorithmic_bytes;
-  out["cache"]["hits_total"] = uint64_t{0};
-  out["cache"]["misses_total"] = uint64_t{0};
-  out["cache"]["hit_rate"] = std::nan("");
-  out["cache"]["local_hit_rates"]["c0"] = std::nan("");
+  // several GPUs: a level-0 read served from the replicated hot set or the GPU's own share is a hit, a read from a
+  // peer's share over NVLink a miss (what the reference would READ over RDMA)
+  auto rate = [](uint64_t hits, uint64_t misses) { return static_cast<double>(hits) / static_cast<double>(hits + misses); };
+  out["cache"]["hits_total"] = st.rows_hot + st.rows_local;
+  out["cache"]["misses_total"] = st.rows_remote;
+  out["cache"]["hit_rate"] = rate(st.rows_hot + st.rows_local, st.rows_remote);
+  for (int g = 0; g < n_gpus; ++g)
+    out["cache"]["local_hit_rates"]["c" + std::to_string(g)] = rate(per_gpu[g].rows_hot + per_gpu[g].rows_local, per_gpu[g].rows_remote);
   out["cache"]["local_size"] = uint64_t{0};
   out["cache"]["cached_nodes"] = uint64_t{0};
   out["cache"]["cache_buckets_size"] = uint64_t{0};
@@ -403,7 +482,7 @@ int main(int argc, char** argv) {
   const size_t dash = cfg.query_suffix.find_first_of('-');
   const std::string zipf = cfg.query_suffix.size() > 1 ? cfg.query_suffix.substr(1, dash == std::string::npos ? std::string::npos : dash - 1) : "";
   auto& meta = out["meta"];
-  meta["compute_nodes"] = 1u;
+  meta["compute_nodes"] = static_cast<uint32_t>(n_gpus);
   meta["memory_nodes"] = num_servers;
   meta["compute_threads"] = cfg.threads;
   meta["coroutines_per_thread"] = cfg.coroutines;
@@ -429,6 +508,7 @@ int main(int argc, char** argv) {
   auto& tj = out["timings"];
   tj["build_c0"] = build_ms;
   tj["query_c0"] = query_ms;
+  for (int g = 1; g < n_gpus; ++g) { tj["build_c" + std::to_string(g)] = build_ms; tj["query_c" + std::to_string(g)] = query_ms; }
   tj["build_max"] = build_ms;
   tj["query_max"] = query_ms;
   tj["placement_fetch"] = 0.0;
@@ -439,6 +519,6 @@ int main(int argc, char** argv) {
   std::cerr << std::endl << "statistics:" << std::endl;
   out.dump(std::cout, 0);
   std::cout << std::endl;
-  shn_index_free(index);
+  for (shn_index* h : handles) shn_index_free(h);
   return 0;
 }

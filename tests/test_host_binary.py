@@ -122,3 +122,35 @@ def test_build_store_load_query_round_trip(tmp_path, ext, ip):
     doc2 = json.loads(r2.stdout)
     assert doc2["queries"]["recall"] == doc["queries"]["recall"] and doc2["queries"]["dist_comps"] == doc["queries"]["dist_comps"]
     assert doc2["build"]["dist_comps"] == 0 and doc2["timings"]["build_c0"] == 0.0
+
+
+@pytest.mark.gpu
+def test_two_gpus_one_partitioned_index(tmp_path):
+    """--gpus 2: memory nodes become HBM partitions (in-process peer pointers), the warm-up pass picks the hot set; the
+    answers must be those of the single-GPU run, and the cache keys of the JSON now carry real hit/miss counts."""
+    import torch
+    if torch.cuda.device_count() < 2 or os.environ.get("SHN_TEST_MULTI_GPU") != "1":
+        pytest.skip("needs two GPUs and SHN_TEST_MULTI_GPU=1 (see DESIGN.md: the in-process cross-device path of "
+                    "shine_b200 --gpus N was fixed after its last run on hardware and is not re-validated yet)")
+    n, nq, dim, m, efc, k, ef = 8000, 400, 32, 16, 100, 10, 64
+    base, queries = datagen.base_and_queries(n, nq + 200, dim)
+    data = tmp_path / "synth-8k"
+    (data / "queries").mkdir(parents=True)
+    write_bin(data / "base.fbin", base)
+    write_bin(data / "queries" / "query-a0.0.fbin", queries[:nq])
+    write_bin(data / "queries" / "warmup-a0.0.fbin", queries[nq:])
+    write_bin(data / "queries" / "groundtruth-a0.0.bin", datagen.bruteforce(base, queries[:nq], 100))
+    common = ["--servers", "mn1", "--initiator", "--data-path", str(data), "--query-suffix", "a0.0", "--threads", "4",
+              "--ef-search", str(ef), "--ef-construction", str(efc), "-k", str(k), "-m", str(m)]
+    one = run(*common, "--store-index")
+    assert one.returncode == 0, one.stderr
+    two = run(*common, "--load-index", "--gpus", "2", "--cache", "--cache-ratio", "10")
+    assert two.returncode == 0, two.stderr
+    d1, d2 = json.loads(one.stdout), json.loads(two.stdout)
+    assert d2["queries"]["recall"] == d1["queries"]["recall"]
+    assert d2["queries"]["dist_comps"] == d1["queries"]["dist_comps"]
+    assert d2["meta"]["compute_nodes"] == 2 and set(d2["queries"]["processed_local"]) == {"c0", "c1"}
+    assert d2["queries"]["processed_local"]["c0"] + d2["queries"]["processed_local"]["c1"] == nq
+    c = d2["cache"]
+    assert c["hits_total"] > 0 and c["misses_total"] > 0 and 0.5 < c["hit_rate"] < 1.0
+    assert set(c["local_hit_rates"]) == {"c0", "c1"} and c["cache_size_ratio"] == 10
