@@ -45,8 +45,9 @@ __device__ __forceinline__ float4 ldg_f4(const float4* p) { return __ldg(p); }
 // own a row, lane t IS the AVX lane j = t, and the 16-byte piece t of every 128-byte block holds exactly the four
 // floats lane j needs from two consecutive chunks.  One warp-wide 128-bit load therefore reads four whole cache
 // lines (4 rows x 128 B) — a quarter of the L1TEX wavefronts of a sector-per-lane-pair layout — and the
-// accumulation needs no shuffles until the final horizontal step.  16 rows are in flight per warp
-// (4 row groups x 4 passes), i.e. 16 independent 128-bit loads per lane at d = 128.
+// accumulation needs no shuffles until the final horizontal step.  With the default SHN_PASSES = 2, 8 rows are in flight
+// per warp (4 row groups x 2 passes), i.e. 8 independent 128-bit loads per lane at d = 128 (96 registers, 5 CTAs/SM —
+// measured better than 16 rows in flight at 128 registers and 4 CTAs/SM).
 // ---------------------------------------------------------------------------------------------------------------
 
 template <bool IP>
@@ -114,7 +115,7 @@ __device__ __forceinline__ float tail_chain(float r, const float4& q, const floa
 // dist(query, row) for rows s_rows[0..cnt) -> s_out[0..cnt).  s_q: the query in shared memory in the stored layout
 // (16-byte aligned).  NCHUNK > 0: the dimension, fixed at compile time (96, 128, 200, 960: the shapes BASELINE.json
 // names); NCHUNK == 0: any dim.
-// PASSES: row groups of 4 evaluated together (4 = 16 rows in flight per warp, the beam-search setting; 1 = the compact
+// PASSES: row groups of 4 evaluated together (SHN_PASSES = 2: 8 rows in flight per warp, the beam-search setting; 1 = the compact
 // variant for the entry point, the greedy descent and the selection heuristic, where register pressure matters more).
 #ifndef SHN_PASSES
 #define SHN_PASSES 2
