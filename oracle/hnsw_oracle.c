@@ -451,3 +451,262 @@ uint32_t orc_select_heuristic(const uint32_t* uids, const float* dists, const fl
   if (distcomps) *distcomps = dc;
   return n_sel;
 }
+
+/* ------------------------------------------------------------------ construction (HNSW::insert, hnsw.hh:40-251)
+ * Single thread, single coroutine, one memory node: the configuration in which the reference's build is deterministic
+ * (SURVEY App. D).  The graph lists come out in the reference's stored order, which search parity depends on:
+ * lists are written in heap-ARRAY order after select_heuristic's make_heap (hnsw.hh:165-175,521), so libstdc++'s
+ * __make_heap / __adjust_heap are restated as well. */
+
+/* std::mt19937 + std::uniform_real_distribution<double>(0,1) as libstdc++ implements them (generate_canonical<double,53>
+ * draws two 32-bit words: (lo + hi * 2^32) / 2^64) */
+typedef struct { uint32_t mt[624]; int idx; } mt19937;
+static void mt_seed(mt19937* g, uint32_t seed) {
+  g->mt[0] = seed;
+  for (int i = 1; i < 624; ++i) g->mt[i] = 1812433253u * (g->mt[i - 1] ^ (g->mt[i - 1] >> 30)) + (uint32_t)i;
+  g->idx = 624;
+}
+static uint32_t mt_next(mt19937* g) {
+  if (g->idx >= 624) {
+    for (int i = 0; i < 624; ++i) {
+      const uint32_t y = (g->mt[i] & 0x80000000u) | (g->mt[(i + 1) % 624] & 0x7fffffffu);
+      g->mt[i] = g->mt[(i + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+    }
+    g->idx = 0;
+  }
+  uint32_t y = g->mt[g->idx++];
+  y ^= y >> 11; y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= y >> 18;
+  return y;
+}
+static double mt_canonical(mt19937* g) {
+  const double lo = (double)mt_next(g), hi = (double)mt_next(g);
+  double r = (lo + hi * 4294967296.0) / 18446744073709551616.0;
+  if (r >= 1.0) r = nextafter(1.0, 0.0);
+  return r;
+}
+
+static void adjust_heap(heap* h, size_t hole, size_t len, entry v) { /* bits/stl_heap.h __adjust_heap */
+  const size_t top = hole;
+  size_t child = hole;
+  while (child < (len - 1) / 2) {
+    child = 2 * (child + 1);
+    if (hcomp(h, h->a[child], h->a[child - 1])) child--;
+    h->a[hole] = h->a[child];
+    hole = child;
+  }
+  if ((len & 1) == 0 && child == (len - 2) / 2) {
+    child = 2 * (child + 1);
+    h->a[hole] = h->a[child - 1];
+    hole = child - 1;
+  }
+  sift_up(h, hole, top, v);
+}
+static void heap_make(heap* h) { /* std::make_heap */
+  const size_t len = h->n;
+  if (len < 2) return;
+  size_t parent = (len - 2) / 2;
+  for (;;) {
+    const entry v = h->a[parent];
+    adjust_heap(h, parent, len, v);
+    if (parent == 0) return;
+    parent--;
+  }
+}
+
+typedef struct {
+  uint32_t n, dim, m, m0;
+  const float* base;
+  uint32_t* level;
+  uint32_t* l0_cnt; uint32_t* l0;          /* [n][m0] */
+  uint64_t* up_base; uint32_t* up_cnt; uint32_t* up; uint64_t n_up, up_cap; /* lists of levels 1..level, m wide */
+  uint32_t ep; int have_ep;
+  uint64_t distcomps;
+  int ip;
+} builder;
+
+static uint32_t* b_list(builder* b, uint32_t row, uint32_t lvl, uint32_t** cnt) {
+  if (lvl == 0) { *cnt = &b->l0_cnt[row]; return b->l0 + (size_t)row * b->m0; }
+  const uint64_t u = b->up_base[row] + (lvl - 1);
+  *cnt = &b->up_cnt[u];
+  return b->up + u * b->m;
+}
+static float b_dist(builder* b, const float* q, uint32_t row) { b->distcomps++; return orc_dist(q, b->base + (size_t)row * b->dim, b->dim, b->ip); }
+
+static int entry_cmp(const void* x, const void* y) { /* heap.hh:53-57 */
+  const entry* l = (const entry*)x; const entry* r = (const entry*)y;
+  if (l->dist == r->dist) return l->row < r->row ? -1 : (l->row > r->row ? 1 : 0);
+  return l->dist < r->dist ? -1 : 1;
+}
+
+/* select_heuristic on a max-heap of (row, distance to the query), hnsw.hh:482-522 */
+static void b_select(builder* b, heap* top, uint32_t m) {
+  if (top->n < m) return;
+  qsort(top->a, top->n, sizeof(entry), entry_cmp);
+  const size_t initial = top->n;
+  size_t selected = 1, consumed = 1;
+  while (selected < m && consumed < initial) {
+    int keep = 1;
+    const entry c = top->a[consumed];
+    for (size_t i = 0; i < selected; ++i) {
+      const float d = b_dist(b, b->base + (size_t)top->a[i].row * b->dim, c.row);
+      if (d < c.dist) { keep = 0; break; }
+    }
+    if (keep) { const entry t = top->a[selected]; top->a[selected] = top->a[consumed]; top->a[consumed] = t; ++selected; }
+    ++consumed;
+  }
+  top->n = selected;
+  heap_make(top);
+}
+
+/* search_level<with_lock>, hnsw.hh:407-476, on `lvl` */
+static void b_search_level(builder* b, const float* q, uint32_t ef, uint32_t lvl, heap* top, heap* next, visited_set* vis) {
+  for (size_t i = 0; i < top->n; ++i) { heap_push(next, top->a[i]); vs_insert(vis, top->a[i].row); }
+  while (next->n > 0) {
+    const entry cand = next->a[0];
+    heap_pop(next);
+    float far = top->a[0].dist;
+    if (cand.dist > far) break;
+    uint32_t* cnt;
+    const uint32_t* list = b_list(b, cand.row, lvl, &cnt);
+    for (uint32_t i = 0; i < *cnt; ++i) {
+      const uint32_t nb = list[i];
+      if (vis->seen[nb]) continue;
+      vs_insert(vis, nb);
+      far = top->a[0].dist;
+      const float d = b_dist(b, q, nb);
+      if (d < far || top->n < ef) { const entry e = {nb, d}; heap_push(next, e); heap_push_k(top, e, ef); }
+    }
+  }
+  next->n = 0;
+  vs_clear(vis);
+}
+
+static void b_insert(builder* b, uint32_t id, uint32_t drawn_level, uint32_t efc, heap* top, heap* next, heap* tmp, visited_set* vis) {
+  const float* q = b->base + (size_t)id * b->dim;
+  const uint32_t m = b->m;
+  if (!b->have_ep) { /* hnsw.hh:56-85: the node that initialises the index is written at level 0 */
+    b->level[id] = 0; b->ep = id; b->have_ep = 1;
+    return;
+  }
+  uint32_t lvl = drawn_level;
+  const uint32_t top_level = b->level[b->ep];
+  const int is_new_level = lvl > top_level;
+  if (is_new_level) lvl = top_level + 1;               /* :106 */
+  b->level[id] = lvl;
+  if (lvl > 0) {                                        /* allocate the upper lists of the new node */
+    if (b->n_up + lvl > b->up_cap) {
+      b->up_cap = (b->n_up + lvl) * 2 + 64;
+      b->up_cnt = (uint32_t*)realloc(b->up_cnt, b->up_cap * sizeof(uint32_t));
+      b->up = (uint32_t*)realloc(b->up, b->up_cap * m * sizeof(uint32_t));
+    }
+    b->up_base[id] = b->n_up;
+    for (uint32_t l = 0; l < lvl; ++l) b->up_cnt[b->n_up + l] = 0;
+    b->n_up += lvl;
+  }
+  const float ep_dist = b_dist(b, q, b->ep);            /* :125-126 */
+  top->n = 0;
+  if (lvl < top_level) {                                /* search_for_one, :129-143 / :332-393 */
+    uint32_t cur = b->ep;
+    float closest = ep_dist;
+    for (uint32_t l = top_level; l > lvl; --l) {
+      int changed;
+      do {
+        changed = 0;
+        uint32_t* cnt;
+        const uint32_t* list = b_list(b, cur, l, &cnt);
+        uint32_t best = cur;
+        for (uint32_t i = 0; i < *cnt; ++i) {
+          const float d = b_dist(b, q, list[i]);
+          if (d < closest) { closest = d; best = list[i]; changed = 1; }
+        }
+        cur = best;
+      } while (changed);
+    }
+    const entry e = {cur, b_dist(b, q, cur)};
+    heap_push(top, e);
+  } else {
+    const entry e = {b->ep, ep_dist};
+    heap_push(top, e);
+  }
+  uint32_t connect_from = lvl;
+  if (is_new_level) --connect_from;                     /* :146-148 */
+  for (int cl = (int)connect_from; cl >= 0; --cl) {
+    b_search_level(b, q, efc, (uint32_t)cl, top, next, vis);
+    b_select(b, top, m);                                /* :163 */
+    uint32_t* own_cnt;
+    uint32_t* own = b_list(b, id, (uint32_t)cl, &own_cnt);
+    *own_cnt = 0;
+    for (size_t i = 0; i < top->n; ++i) own[(*own_cnt)++] = top->a[i].row;   /* heap-array order, :170-172 */
+    const uint32_t m_max = cl == 0 ? b->m0 : m;
+    for (size_t i = 0; i < top->n; ++i) {               /* :180-225 */
+      const uint32_t nb = top->a[i].row;
+      const float nb_dist = top->a[i].dist;
+      uint32_t* cnt;
+      uint32_t* list = b_list(b, nb, (uint32_t)cl, &cnt);
+      if (*cnt < m_max) {
+        list[(*cnt)++] = id;
+      } else {
+        tmp->n = 0;
+        const entry self = {id, nb_dist};
+        heap_push(tmp, self);
+        for (uint32_t j = 0; j < *cnt; ++j) {
+          const entry o = {list[j], b_dist(b, b->base + (size_t)nb * b->dim, list[j])};
+          heap_push(tmp, o);
+        }
+        b_select(b, tmp, m_max);
+        *cnt = 0;
+        for (size_t j = 0; j < tmp->n; ++j) list[(*cnt)++] = tmp->a[j].row;
+      }
+    }
+    while (cl > 0 && top->n > 1) heap_pop(top);         /* :228-230 */
+  }
+  if (is_new_level) b->ep = id;                         /* :237-247 */
+}
+
+int orc_build(const float* base, uint32_t n, uint32_t dim, uint32_t m, uint32_t efc, uint32_t seed, int ip, uint8_t** dump,
+              uint64_t* dump_size, uint64_t* distcomps) {
+  if (!base || n == 0 || m < 2 || !dump || !dump_size) return -1;
+  builder b; memset(&b, 0, sizeof b);
+  b.n = n; b.dim = dim; b.m = m; b.m0 = 2 * m; b.base = base; b.ip = ip;
+  b.level = (uint32_t*)calloc(n, sizeof(uint32_t));
+  b.l0_cnt = (uint32_t*)calloc(n, sizeof(uint32_t));
+  b.l0 = (uint32_t*)malloc((size_t)n * b.m0 * sizeof(uint32_t));
+  b.up_base = (uint64_t*)calloc(n, sizeof(uint64_t));
+  mt19937 gen; mt_seed(&gen, seed);
+  const double norm = 1.0 / log((double)m);
+  heap top = {0, 0, 0, 1}, next = {0, 0, 0, 0}, tmp = {0, 0, 0, 1};
+  visited_set vis = {(uint8_t*)calloc(n, 1), 0, 0, 0};
+  for (uint32_t id = 0; id < n; ++id) {
+    const uint32_t lvl = (uint32_t)floor(-log(mt_canonical(&gen)) * norm);   /* :48 — drawn for every insert, the first too */
+    b_insert(&b, id, lvl, efc, &top, &next, &tmp, &vis);
+  }
+  /* emit what memory node 1 would hold: nodes in allocation (= insertion) order (memory_node.hh:14-26,187-195) */
+  uint64_t* off = (uint64_t*)malloc((size_t)n * sizeof(uint64_t));
+  uint64_t cur = 16;
+  for (uint32_t r = 0; r < n; ++r) { off[r] = cur; cur += node_alloc_bytes(dim, m, b.level[r]); }
+  uint8_t* d = (uint8_t*)calloc(cur, 1);
+  memcpy(d, &cur, 8);
+  memcpy(d + 8, &off[b.ep], 8);                          /* RemotePtr: memory node 0, byte offset */
+  for (uint32_t r = 0; r < n; ++r) {
+    uint8_t* nd = d + off[r];
+    const uint64_t header = r == b.ep ? (1ull << 16) : 0;
+    memcpy(nd, &header, 8); memcpy(nd + 8, &r, 4); memcpy(nd + 12, &b.level[r], 4);
+    memcpy(nd + 16, base + (size_t)r * dim, 4 * (size_t)dim);
+    uint8_t* l0 = nd + node_header_bytes(dim);
+    memcpy(l0, &b.l0_cnt[r], 4);
+    for (uint32_t j = 0; j < b.l0_cnt[r]; ++j) memcpy(l0 + 4 + 8 * (size_t)j, &off[b.l0[(size_t)r * b.m0 + j]], 8);
+    for (uint32_t l = 1; l <= b.level[r]; ++l) {
+      uint8_t* lu = l0 + list0_bytes(m) + (size_t)(l - 1) * listu_bytes(m);
+      const uint64_t u = b.up_base[r] + (l - 1);
+      memcpy(lu, &b.up_cnt[u], 4);
+      for (uint32_t j = 0; j < b.up_cnt[u]; ++j) memcpy(lu + 4 + 8 * (size_t)j, &off[b.up[u * m + j]], 8);
+    }
+  }
+  *dump = d; *dump_size = cur;
+  if (distcomps) *distcomps = b.distcomps;
+  free(off); free(b.level); free(b.l0_cnt); free(b.l0); free(b.up_base); free(b.up_cnt); free(b.up);
+  free(top.a); free(next.a); free(tmp.a); free(vis.seen); free(vis.touched);
+  return 0;
+}
+
+void orc_free_buffer(void* p) { free(p); }

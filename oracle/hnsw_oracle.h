@@ -4,7 +4,9 @@
  * checker, never the product.  Every function cites the reference file:line it restates
  * (paths relative to /root/reference).  Parity status: PINNED — checked against the reference's own
  * code (oracle/_ref/libshine_ref.so, built from /root/reference unmodified) by tests/test_oracle_pin.py
- * and against the committed fixtures in tests/golden/ that were generated from it.
+ * and against the committed fixtures in tests/golden/ that were generated from it: knn (ids in heap-array order,
+ * distance bits, counters), distances, select_heuristic (selected set, distcomps) and insert (the whole graph of a
+ * single-coroutine build, lists in stored order, distcomps).
  */
 #ifndef HNSW_ORACLE_H
 #define HNSW_ORACLE_H
@@ -55,6 +57,13 @@ int orc_knn(const orc_index*, const float* queries, uint32_t nq, uint32_t k, uin
 uint32_t orc_select_heuristic(const uint32_t* uids, const float* dists, const float* vectors /*[c][dim]*/,
                               uint32_t c, uint32_t dim, uint32_t m, int ip, uint32_t* selected,
                               uint64_t* distcomps);
+
+/* HNSW::insert (src/hnsw/hnsw.hh:40-251) for ids 0..n-1 in order, one thread, one coroutine, one memory node — the
+ * configuration in which the reference's build is deterministic.  *dump (free with orc_free_buffer) is what memory node 1
+ * would write (src/memory_node.hh:187-195); lists are in the reference's stored order. */
+int orc_build(const float* base, uint32_t n, uint32_t dim, uint32_t m, uint32_t efc, uint32_t seed, int ip, uint8_t** dump,
+              uint64_t* dump_size, uint64_t* distcomps);
+void orc_free_buffer(void* p);
 
 #ifdef __cplusplus
 }

@@ -112,3 +112,19 @@ def sorted_results(ids, dists):
     """Sort each row ascending by (distance, id): the canonical form results are compared in."""
     order = np.lexsort((ids, dists), axis=1)
     return np.take_along_axis(ids, order, 1), np.take_along_axis(dists, order, 1)
+
+
+def build(base, m=16, efc=200, seed=1234, ip=False):
+    """HNSW::insert restated (single thread / single coroutine / one memory node).  Returns (dump bytes, distcomps)."""
+    base = np.ascontiguousarray(base, dtype=np.float32)
+    n, dim = base.shape
+    dump = C.POINTER(C.c_uint8)()
+    size = C.c_uint64()
+    dc = C.c_uint64()
+    rc = lib().orc_build(_p(base), C.c_uint32(n), C.c_uint32(dim), C.c_uint32(m), C.c_uint32(efc), C.c_uint32(seed),
+                         C.c_int(int(ip)), C.byref(dump), C.byref(size), C.byref(dc))
+    if rc != 0:
+        raise ValueError("orc_build: invalid arguments")
+    out = C.string_at(dump, size.value)
+    lib().orc_free_buffer(dump)
+    return out, dc.value

@@ -124,3 +124,28 @@ def test_select_heuristic_matches_reference_live(c, dim, m, ip):
     r_sel, r_dc = shine_ref.select_heuristic(uids, d, vec, m, ip)
     o_sel, o_dc = hnsw_oracle.select_heuristic(uids, d, vec, m, ip)
     assert sorted(r_sel.tolist()) == sorted(o_sel.tolist()) and r_dc == o_dc
+
+
+@needs_ref
+@pytest.mark.parametrize("n,dim,m,efc,ip", [(300, 16, 4, 20, False), (2000, 32, 16, 100, False), (1500, 40, 8, 60, True),
+                                            (700, 128, 32, 50, False), (1, 8, 4, 10, False), (12, 8, 2, 10, False)])
+def test_build_restatement_is_the_reference_build(n, dim, m, efc, ip):
+    """orc_build (HNSW::insert restated) against the reference's own single-thread / single-coroutine build, which is
+    deterministic: identical levels, identical level-0 and upper lists IN STORED ORDER, identical entry point, identical
+    dump size and distance-computation count."""
+    base, queries = datagen.base_and_queries(n, 20, dim, normalize=ip)
+    ref, rst, _ = shine_ref.build(base, m=m, efc=efc, seed=1234, ip=ip, threads=1, coroutines=1)
+    mine, dc = hnsw_oracle.build(base, m=m, efc=efc, seed=1234, ip=ip)
+    assert len(mine) == len(ref[0]) and dc == rst["distcomps"]
+    a, b = hnsw_oracle.Index(ref, dim, m), hnsw_oracle.Index([mine], dim, m)
+    assert a.entry_row == b.entry_row and a.max_level == b.max_level
+    ea, eb = a.export(), b.export()
+    for key in ea:
+        assert (ea[key] == eb[key]).all(), key
+    for r in np.nonzero(ea["level"] > 0)[0]:
+        for l in range(1, ea["level"][r] + 1):
+            assert np.array_equal(a.neighbors(int(r), l), b.neighbors(int(r), l))
+    if n >= 100:  # and therefore the same search results
+        ra = a.knn(queries, 10, 50, ip=ip)
+        rb = b.knn(queries, 10, 50, ip=ip)
+        assert (ra[0] == rb[0]).all()
