@@ -6,5 +6,5 @@ The directory name is not an importable identifier: load it with `load_package()
 put this directory on sys.path and `import shn`.
 """
 from . import parallel, shn  # noqa: F401
-from .shn import (Index, ShnError, bruteforce_topk, bruteforce_topk_device, build_library, draw_levels, library_path, route_queries,
+from .shn import (Index, Router, ShnError, bruteforce_topk, bruteforce_topk_device, build_library, device_view, draw_levels, library_path, route_queries,
                   repartition_dumps, set_build_option)  # noqa: F401

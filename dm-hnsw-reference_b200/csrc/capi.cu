@@ -7,9 +7,7 @@
 #include <string>
 #include <vector>
 
-#include "../../include/shn.h"
-#include "engine.h"
-#include "vmm.h"
+#include "handle.h"
 
 using namespace shn;
 
@@ -19,6 +17,9 @@ thread_local std::string g_err;
 // construction knobs (shn_set_build_option): process-wide, read when shn_index_build* starts
 uint32_t g_build_batch_max = 0, g_build_batch_div = 0;
 
+}  // namespace
+
+namespace shn {
 int fail(int code, const char* fmt, ...) {
   char buf[1024];
   va_list ap;
@@ -28,83 +29,9 @@ int fail(int code, const char* fmt, ...) {
   g_err = buf;
   return code;
 }
+}  // namespace shn
 
-#define CU(call)                                                                                   \
-  do {                                                                                             \
-    cudaError_t e__ = (call);                                                                      \
-    if (e__ != cudaSuccess) return fail(SHN_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e__));  \
-  } while (0)
-
-template <class T>
-struct DevBuf {
-  T* p = nullptr;
-  size_t n = 0;
-  cudaError_t ensure(size_t want) {
-    if (want <= n) return cudaSuccess;
-    if (p) cudaFree(p);
-    p = nullptr; n = 0;
-    cudaError_t e = cudaMalloc(&p, want * sizeof(T));
-    if (e == cudaSuccess) n = want;
-    return e;
-  }
-  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
-};
-
-}  // namespace
-
-struct shn_index {
-  int gpu = 0;
-  int num_sms = 0;
-  shn_metric metric = SHN_L2;
-  cudaStream_t stream = nullptr;
-  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-
-  // graph in HBM (graph.h)
-  uint32_t n = 0, dim = 0, m = 0, row_f4 = 0, ep_row = kInvalid, max_level = 0;
-  uint64_t n_up = 0;
-  float4* d_vec = nullptr;
-  uint32_t* d_l0 = nullptr;
-  uint32_t* d_up_base = nullptr;
-  uint32_t* d_up = nullptr;
-  uint32_t* d_ext_id = nullptr;
-  uint32_t* d_level = nullptr;
-  uint64_t hbm_bytes = 0, dump_bytes = 0;
-
-  // scratch
-  SearchWorkspace ws;
-  DevBuf<uint32_t> ovf;
-  DevBuf<float> q_stage, dist_stage;
-  DevBuf<uint32_t> id_stage;
-  int warps_per_sm = 0;
-  uint32_t vis_cap = 0;
-  shn_stats build_stats{};
-  // partitioned handle (shn_index_partition): d_vec / d_l0 / d_up_base hold the replicated hot set
-  uint32_t hot = 0, world = 1, rank = 0, own = 0, attached = 1, clustered = 0;
-  uint32_t part_begin[9] = {0};
-  float4* d_own_vec = nullptr;
-  uint32_t* d_own_l0 = nullptr;
-  const float4** d_part_vec = nullptr;   // device table [world]
-  const uint32_t** d_part_l0 = nullptr;
-  VmmBlock own_vec_blk, own_l0_blk;      // this GPU's share (exportable as POSIX fds)
-  VmmBlock peer_vec_blk[8], peer_l0_blk[8];  // shares of other processes mapped here
-  uint32_t* d_visits = nullptr;          // [n] when visit counting is on
-  bool built = false;
-
-  DeviceGraph view() const {
-    DeviceGraph g;
-    g.vec = d_vec; g.l0 = d_l0; g.up_base = d_up_base; g.up = d_up; g.ext_id = d_ext_id;
-    g.n = n; g.dim = dim; g.m = m; g.m0 = 2 * m; g.row_f4 = row_f4; g.ep_row = ep_row; g.ep_level = max_level_of_ep;
-    g.hot = world > 1 ? hot : n; g.world = world; g.rank = rank;
-    g.part_vec = d_part_vec; g.part_l0 = d_part_l0; g.visit_count = d_visits;
-    g.clustered = clustered;
-    for (int i = 0; i < 9; ++i) g.part_begin[i] = part_begin[i];
-    return g;
-  }
-  uint32_t max_level_of_ep = 0;
-};
-
-namespace {
-
+namespace shn {
 int select_device(int gpu_id, int* num_sms) {
   int count = 0;
   cudaError_t e = cudaGetDeviceCount(&count);
@@ -119,6 +46,9 @@ int select_device(int gpu_id, int* num_sms) {
   *num_sms = prop.multiProcessorCount;
   return SHN_OK;
 }
+}  // namespace shn
+
+namespace {
 
 // Move a parsed graph into HBM in the layout of graph.h.
 int upload(shn_index* ix, const HostGraph& g) {
@@ -199,6 +129,7 @@ int new_handle(shn_index** out, int gpu_id, shn_metric metric) {
   ix->gpu = gpu_id; ix->num_sms = sms; ix->metric = metric;
   cudaError_t e = cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking);
   for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreate(&ix->ev[i]);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ix->ev_last, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaMalloc(&ix->ws.counter, sizeof(uint32_t));
   if (e == cudaSuccess) e = cudaMalloc(&ix->ws.totals, kNumTotals * sizeof(unsigned long long));
   if (e != cudaSuccess) {
@@ -222,6 +153,10 @@ bool read_file(const char* path, std::vector<uint8_t>& out, std::string& err) {
   if (got != out.size()) { err = std::string("short read on ") + path; return false; }
   return true;
 }
+
+}  // namespace
+
+namespace shn {
 
 // Overflow tables: one per warp slot of the launch, sized from ef.
 int prepare_workspace(shn_index* ix, const SearchConfig& cfg, uint32_t nq) {
@@ -264,15 +199,20 @@ void fill_stats(const shn_index* ix, const unsigned long long* t, uint64_t nq, s
 }
 
 int run_search(shn_index* ix, const float* d_queries, uint64_t nq, uint32_t k, uint32_t ef, uint32_t* d_ids, float* d_dists,
-               uint32_t* d_per_query, cudaStream_t stream, bool timed) {
+               uint32_t* d_per_query, cudaStream_t stream, bool timed, const RoutedIo* io) {
   SearchConfig cfg;
   cfg.k = k; cfg.ef = ef; cfg.ip = ix->metric == SHN_IP; cfg.warps_per_sm = ix->warps_per_sm; cfg.num_sms = ix->num_sms; cfg.vis_cap = ix->vis_cap;
   int rc = prepare_workspace(ix, cfg, static_cast<uint32_t>(nq));
   if (rc != SHN_OK) return rc;
+  // One launch per handle at a time: the work cursor, the totals and the overflow tables are per handle.  A launch on
+  // another stream first waits for the previous one (a caller that alternates streams is serialised, not corrupted).
+  if (ix->launched) CU(cudaStreamWaitEvent(stream, ix->ev_last, 0));
   if (timed) CU(cudaEventRecord(ix->ev[1], stream));
-  cudaError_t e = search_launch(ix->view(), cfg, d_queries, static_cast<uint32_t>(nq), d_ids, d_dists, d_per_query, ix->ws, stream);
+  cudaError_t e = search_launch(ix->view(), cfg, d_queries, static_cast<uint32_t>(nq), d_ids, d_dists, d_per_query, ix->ws, stream, io);
   if (e != cudaSuccess) return fail(SHN_ERR_CUDA, "search_launch: %s", cudaGetErrorString(e));
   if (timed) CU(cudaEventRecord(ix->ev[2], stream));
+  CU(cudaEventRecord(ix->ev_last, stream));
+  ix->launched = true;
   return SHN_OK;
 }
 
@@ -286,6 +226,9 @@ int check_search_args(const shn_index* ix, uint64_t nq, uint32_t k, uint32_t ef)
   return SHN_OK;
 }
 
+}  // namespace shn
+
+namespace {
 }  // namespace
 
 extern "C" {
@@ -496,6 +439,7 @@ void shn_index_free(shn_index* ix) {
   cudaFree(ix->ws.counter); cudaFree(ix->ws.totals);
   ix->ovf.release(); ix->q_stage.release(); ix->dist_stage.release(); ix->id_stage.release();
   for (auto& e : ix->ev) if (e) cudaEventDestroy(e);
+  if (ix->ev_last) cudaEventDestroy(ix->ev_last);
   if (ix->stream) cudaStreamDestroy(ix->stream);
   delete ix;
 }
@@ -531,7 +475,7 @@ int shn_search_device(shn_index* ix, const float* d_queries, uint64_t nq, uint32
   if (!d_queries || !d_out_ids) return fail(SHN_ERR_ARG, "null buffer");
   CU(cudaSetDevice(ix->gpu));
   cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ix->stream;
-  rc = run_search(ix, d_queries, nq, k, ef, d_out_ids, d_out_dists, d_per_query_counters, s, stats != nullptr);
+  rc = run_search(ix, d_queries, nq, k, ef, d_out_ids, d_out_dists, d_per_query_counters, s, stats != nullptr, nullptr);
   if (rc != SHN_OK) return rc;
   if (stats) {
     unsigned long long t[kNumTotals];
@@ -560,7 +504,7 @@ int shn_search(shn_index* ix, const float* queries, uint64_t nq, uint32_t k, uin
   cudaStream_t s = ix->stream;
   CU(cudaEventRecord(ix->ev[0], s));
   CU(cudaMemcpyAsync(ix->q_stage.p, queries, nq * ix->dim * sizeof(float), cudaMemcpyHostToDevice, s));
-  rc = run_search(ix, ix->q_stage.p, nq, k, ef, ix->id_stage.p, ix->dist_stage.p, nullptr, s, true);
+  rc = run_search(ix, ix->q_stage.p, nq, k, ef, ix->id_stage.p, ix->dist_stage.p, nullptr, s, true, nullptr);
   if (rc != SHN_OK) return rc;
   CU(cudaMemcpyAsync(out_ids, ix->id_stage.p, nq * k * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
   if (out_dists) CU(cudaMemcpyAsync(out_dists, ix->dist_stage.p, nq * k * sizeof(float), cudaMemcpyDeviceToHost, s));
@@ -587,7 +531,8 @@ int shn_index_count_visits(shn_index* ix, int enable) {
   CU(cudaStreamSynchronize(ix->stream));
   if (!enable) { cudaFree(ix->d_visits); ix->d_visits = nullptr; return SHN_OK; }
   if (!ix->d_visits) CU(cudaMalloc(&ix->d_visits, static_cast<size_t>(ix->n) * sizeof(uint32_t)));
-  CU(cudaMemset(ix->d_visits, 0, static_cast<size_t>(ix->n) * sizeof(uint32_t)));
+  CU(cudaMemsetAsync(ix->d_visits, 0, static_cast<size_t>(ix->n) * sizeof(uint32_t), ix->stream));
+  CU(cudaStreamSynchronize(ix->stream));
   return SHN_OK;
 }
 
@@ -596,8 +541,11 @@ int shn_index_visit_counts(shn_index* ix, uint32_t* d_counts, int write_back) {
   if (!ix->d_visits) return fail(SHN_ERR_STATE, "visit counting is off");
   CU(cudaSetDevice(ix->gpu));
   CU(cudaStreamSynchronize(ix->stream));
-  if (write_back) CU(cudaMemcpy(ix->d_visits, d_counts, static_cast<size_t>(ix->n) * sizeof(uint32_t), cudaMemcpyDeviceToDevice));
-  else CU(cudaMemcpy(d_counts, ix->d_visits, static_cast<size_t>(ix->n) * sizeof(uint32_t), cudaMemcpyDeviceToDevice));
+  // on the handle's stream and complete on return (a device-to-device cudaMemcpy on the legacy stream is neither ordered
+  // with the caller's non-blocking streams nor finished when it returns)
+  if (write_back) CU(cudaMemcpyAsync(ix->d_visits, d_counts, static_cast<size_t>(ix->n) * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ix->stream));
+  else CU(cudaMemcpyAsync(d_counts, ix->d_visits, static_cast<size_t>(ix->n) * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ix->stream));
+  CU(cudaStreamSynchronize(ix->stream));
   return SHN_OK;
 }
 
@@ -738,9 +686,18 @@ int shn_placement_fit(const shn_index* full, int world, uint32_t seed, double sl
   }
   if (rows.size() < static_cast<size_t>(world)) return fail(SHN_ERR_ARG, "fewer nodes than partitions");
   std::vector<float> sample(rows.size() * dimS);
-  for (size_t i = 0; i < rows.size(); ++i)
-    CU(cudaMemcpy(sample.data() + i * dimS, reinterpret_cast<const float*>(full->d_vec) + static_cast<size_t>(rows[i]) * dimS,
-                  dimS * sizeof(float), cudaMemcpyDeviceToHost));
+  {  // one gather kernel + one copy
+    uint32_t* d_rows = nullptr;
+    float4* d_sample = nullptr;
+    cudaError_t ge = cudaMalloc(&d_rows, rows.size() * sizeof(uint32_t));
+    if (ge == cudaSuccess) ge = cudaMalloc(&d_sample, sample.size() * sizeof(float));
+    if (ge == cudaSuccess) ge = cudaMemcpyAsync(d_rows, rows.data(), rows.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, full->stream);
+    if (ge == cudaSuccess) ge = gather_rows(full->d_vec, d_rows, static_cast<uint32_t>(rows.size()), full->row_f4, d_sample, full->stream);
+    if (ge == cudaSuccess) ge = cudaMemcpyAsync(sample.data(), d_sample, sample.size() * sizeof(float), cudaMemcpyDeviceToHost, full->stream);
+    if (ge == cudaSuccess) ge = cudaStreamSynchronize(full->stream);
+    cudaFree(d_rows); cudaFree(d_sample);
+    if (ge != cudaSuccess) return fail(SHN_ERR_CUDA, "fetching the k-means sample: %s", cudaGetErrorString(ge));
+  }
   std::vector<float> cent;
   kmeans_host(sample, static_cast<uint32_t>(rows.size()), dimS, world, seed, full->metric == SHN_IP, cent);
   float* d_cent = nullptr;

@@ -12,7 +12,7 @@ namespace shn {
 
 // Indices into the device-side totals array (u64 each), summed over the queries of one launch.
 enum Total { kDistcomps = 0, kVisitedUpper, kVisitedL0, kListsL0, kListsUpper, kOverflowQueries, kFailedQueries,
-             kRowsHot, kRowsLocal, kRowsRemote, kNumTotals };
+             kRowsHot, kRowsLocal, kRowsRemote, kProcessed, kNumTotals };
 
 // Per-query counter record written when the caller asks for it (shn_search_device per_query_counters).
 constexpr int kPerQueryWords = 6;  // distcomps, visited_nodes, visited_nodes_l0, lists_l0, lists_upper, overflow
@@ -22,6 +22,17 @@ struct SearchWorkspace {
   unsigned long long* totals = nullptr;   // [kNumTotals]
   uint32_t* ovf = nullptr;                // [ovf_slots][ovf_cap], all kInvalid at rest
   uint32_t ovf_cap = 0, ovf_slots = 0;
+};
+
+// Routed I/O (router.cu): the queries of a launch come from this GPU's inbox segments (one per source GPU, already in the
+// stored row order) and every result row goes straight to the landing buffer of the query's home GPU, at the home slot.
+struct RoutedIo {
+  const float4* in_rows = nullptr;      // [world][cap][row_f4]; nullptr = plain I/O
+  const uint32_t* in_tags = nullptr;    // [world][cap]: home slot of each query
+  const uint32_t* in_counts = nullptr;  // [world]: queries received from each source GPU
+  uint32_t cap = 0, world = 0;
+  uint32_t* const* out_ids = nullptr;   // device tables [world] (local or peer-mapped)
+  float* const* out_dists = nullptr;
 };
 
 struct SearchConfig {
@@ -40,7 +51,7 @@ cudaError_t search_plan(const DeviceGraph& g, const SearchConfig& cfg, uint32_t 
 // stream first.  No synchronisation.
 cudaError_t search_launch(const DeviceGraph& g, const SearchConfig& cfg, const float* d_queries, uint32_t nq,
                           uint32_t* d_ids, float* d_dists, uint32_t* d_per_query, SearchWorkspace& ws,
-                          cudaStream_t stream);
+                          cudaStream_t stream, const RoutedIo* io = nullptr);
 
 // Exact top-k by brute force over base[n][dim] (row stride = dim floats): ids are row numbers.  Synchronises.
 cudaError_t bruteforce_launch(const float* d_base, uint64_t n, const float* d_queries, uint32_t nq, uint32_t dim, bool ip,
@@ -68,6 +79,7 @@ struct PartitionJob {
   uint32_t *hot_l0 = nullptr, *own_l0 = nullptr, *hot_up_base = nullptr, *up = nullptr, *ext_id = nullptr;
 };
 cudaError_t partition_arrays(const PartitionJob& job, cudaStream_t stream);
+cudaError_t gather_rows(const float4* src, const uint32_t* d_rows, uint32_t count, uint32_t row_f4, float4* dst, cudaStream_t s);
 cudaError_t probe_gather(const float4* src, uint32_t nrows, uint32_t row_f4, double* gbs, cudaStream_t stream);
 
 // ---- placement and routing (placement.cu)

@@ -111,14 +111,17 @@ __device__ __forceinline__ void locate_row(const DeviceGraph& g, uint32_t row, u
     idx = o / g.world;
   }
 }
+// PART = false: the handle holds every row (one GPU, or the builder): no placement test in the instruction stream
+template <bool PART>
 __device__ __forceinline__ const float4* vec_row(const DeviceGraph& g, uint32_t row) {
-  if (row < g.hot) return g.vec + static_cast<size_t>(row) * g.row_f4;
+  if (!PART || row < g.hot) return g.vec + static_cast<size_t>(row) * g.row_f4;
   uint32_t part, idx;
   locate_row(g, row, part, idx);
   return g.part_vec[part] + static_cast<size_t>(idx) * g.row_f4;
 }
+template <bool PART>
 __device__ __forceinline__ const uint32_t* l0_row(const DeviceGraph& g, uint32_t row) {
-  if (row < g.hot) return g.l0 + static_cast<size_t>(row) * g.m0;
+  if (!PART || row < g.hot) return g.l0 + static_cast<size_t>(row) * g.m0;
   uint32_t part, idx;
   locate_row(g, row, part, idx);
   return g.part_l0[part] + static_cast<size_t>(idx) * g.m0;

@@ -86,6 +86,13 @@ cudaError_t partition_arrays(const PartitionJob& j, cudaStream_t s) {
 }
 
 
+// dst[i] = src[rows[i]] (whole rows of row_f4 float4): one launch instead of one copy per row
+cudaError_t gather_rows(const float4* src, const uint32_t* d_rows, uint32_t count, uint32_t row_f4, float4* dst, cudaStream_t s) {
+  if (count == 0) return cudaSuccess;
+  gather_rows_kernel<<<grid_for(static_cast<uint64_t>(count) * 32, 256), 256, 0, s>>>(src, d_rows, 0, 1, count, row_f4, dst);
+  return cudaGetLastError();
+}
+
 cudaError_t probe_gather(const float4* src, uint32_t nrows, uint32_t row_f4, double* gbs, cudaStream_t s) {
   float* out = nullptr;
   cudaError_t e = cudaMalloc(&out, 4);

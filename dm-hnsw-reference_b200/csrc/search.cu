@@ -15,10 +15,17 @@
 namespace shn {
 namespace {
 
+// CTA shape: 4 warps, 5 CTAs per SM -> 20 query warps per SM at 96 registers.  Measured on B200 (SIFT10M-shaped, 1 M queries,
+// ef 16/64/128/256, M q/s): 4x5 18.3/6.65/2.92/1.35, 4x6 (80 registers, spills) 18.2/5.76/2.46/1.15, 8x3 18.3/5.74/2.41/1.10,
+// 8x4 (64 registers) 12.7/3.55/1.95/0.85 — the kernel is bound by memory latency x bytes in flight per warp, and squeezing
+// the row registers costs more than the extra warps bring.
+#ifndef SHN_WARPS_PER_BLOCK
+#define SHN_WARPS_PER_BLOCK 4
+#endif
 #ifndef SHN_MIN_BLOCKS
 #define SHN_MIN_BLOCKS 5
 #endif
-constexpr int kWarpsPerBlock = 4;
+constexpr int kWarpsPerBlock = SHN_WARPS_PER_BLOCK;
 
 struct SearchParams {
   DeviceGraph g;
@@ -31,35 +38,40 @@ struct SearchParams {
   unsigned long long* totals;
   uint32_t* ovf;
   uint32_t vis_cap, vis_limit, ovf_cap, ovf_limit;
-  uint32_t q_floats, ef_cap;  // shared-memory strides
+  uint32_t q_floats, ef_cap, list_cap;  // shared-memory strides
+  RoutedIo io;
 };
 
-__host__ __device__ inline size_t warp_smem_bytes(uint32_t q_floats, uint32_t ef_cap, uint32_t vis_cap) {
-  return 4ull * (q_floats + 2 * ef_cap + 2 * kMaxList + vis_cap);
+// per warp: launch totals | query | row/distance staging (one list) | queue distances | queue ids | visited table
+constexpr uint32_t kTotalsBytes = (kNumTotals * 8 + 15) / 16 * 16;
+__host__ __device__ inline size_t warp_smem_bytes(uint32_t q_floats, uint32_t ef_cap, uint32_t list_cap, uint32_t vis_cap) {
+  return kTotalsBytes + 4ull * (q_floats + 2 * list_cap + 2 * ef_cap + vis_cap);
 }
 
-template <bool IP, int NCHUNK>
+template <bool IP, int NCHUNK, bool PART>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, SHN_MIN_BLOCKS) search_kernel(const SearchParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const DeviceGraph& g = p.g;
 
-  unsigned char* base = smem_raw + warp * warp_smem_bytes(p.q_floats, p.ef_cap, p.vis_cap);
-  float* s_q = reinterpret_cast<float*>(base);
-  float* qd = s_q + p.q_floats;
+  const uint32_t q_floats = NCHUNK > 0 ? row_stride_f4(NCHUNK) * 4u : p.q_floats;
+  unsigned char* base = smem_raw + warp * warp_smem_bytes(q_floats, p.ef_cap, p.list_cap, p.vis_cap);
+  // the launch totals live in shared memory (11 x 64 bit per warp would otherwise sit in registers for the whole kernel)
+  unsigned long long* s_tot = reinterpret_cast<unsigned long long*>(base);
+  float* s_q = reinterpret_cast<float*>(base + kTotalsBytes);
+  uint32_t* s_rows = reinterpret_cast<uint32_t*>(s_q + q_floats);
+  float* s_dist = reinterpret_cast<float*>(s_rows + p.list_cap);
+  float* qd = s_dist + p.list_cap;
   uint32_t* qi = reinterpret_cast<uint32_t*>(qd + p.ef_cap);
-  uint32_t* s_rows = qi + p.ef_cap;
-  float* s_dist = reinterpret_cast<float*>(s_rows + kMaxList);
   VisitedSet vis;
-  vis.tab = reinterpret_cast<uint32_t*>(s_dist + kMaxList);
+  vis.tab = qi + p.ef_cap;
   vis.cap = p.vis_cap; vis.limit = p.vis_limit;
   vis.ovf = p.ovf + static_cast<size_t>(blockIdx.x * kWarpsPerBlock + warp) * p.ovf_cap;
   vis.ovf_cap = p.ovf_cap; vis.ovf_limit = p.ovf_limit;
   vis.count = 0; vis.ovf_count = 0; vis.failed = false;
-
-  unsigned long long t_dist = 0, t_vup = 0, t_vl0 = 0, t_l0 = 0, t_lup = 0, t_ovf = 0, t_fail = 0, t_hot = 0, t_local = 0, t_remote = 0;
-  const uint32_t ef = p.ef;
+  if (lane < kNumTotals) s_tot[lane] = 0ull;
+  __syncwarp();
 
   for (;;) {
     uint32_t q = 0;
@@ -67,14 +79,29 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, SHN_MIN_BLOCKS) search_ke
     q = __shfl_sync(kFull, q, 0);
     if (q >= p.nq) break;
 
-    // stage the query (database slot components, io/database.hh:17-21)
-    const float* gq = p.queries + static_cast<size_t>(q) * g.dim;
-    for (uint32_t j = lane; j < p.q_floats; j += 32) s_q[j] = 0.f;
-    __syncwarp();
-    for (uint32_t j = lane; j < g.dim; j += 32) s_q[row_pos(g.dim, j)] = __ldg(gq + j);  // stored order (graph.h)
+    if (p.io.in_rows) {
+      // routed: the q-th query of this GPU's inbox = slot j of source segment `src`; it arrived in the stored order
+      uint32_t src = 0, j = q;
+      while (src < p.io.world) {
+        const uint32_t c = __ldg(p.io.in_counts + src);
+        if (j < c) break;
+        j -= c; ++src;
+      }
+      if (src == p.io.world) break;  // past the last received query
+      const float4* row = p.io.in_rows + (static_cast<size_t>(src) * p.io.cap + j) * g.row_f4;
+      for (uint32_t f = lane; f < g.row_f4; f += 32) reinterpret_cast<float4*>(s_q)[f] = row[f];
+    } else {
+      // stage the query (database slot components, io/database.hh:17-21)
+      const float* gq = p.queries + static_cast<size_t>(q) * g.dim;
+      for (uint32_t j = lane; j < q_floats; j += 32) s_q[j] = 0.f;
+      __syncwarp();
+      for (uint32_t j = lane; j < g.dim; j += 32) s_q[row_pos(g.dim, j)] = __ldg(gq + j);  // stored order (graph.h)
+    }
     visited_reset(vis, lane);
 
-    uint32_t c_dist = 0, c_vup = 0, c_vl0 = 0, c_l0 = 0, c_lup = 0;
+    // distcomps is not tracked separately: every visited node costs one distance computation, the entry point two
+    // (hnsw.hh:272 and :286) -> distcomps = visited_nodes + visited_nodes_l0 + 1
+    uint32_t c_unused = 0, c_vup = 0, c_vl0 = 0, c_l0 = 0, c_lup = 0;
 
     // hnsw.hh:261-272 — the entry point and its distance
     uint32_t cur = g.ep_row;
@@ -83,16 +110,14 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, SHN_MIN_BLOCKS) search_ke
     __syncwarp();
     eval_rows<IP, NCHUNK, SHN_SMALL_PASSES>(g, s_q, s_rows, 1, s_dist, lane);
     float closest = s_dist[0];
-    ++c_dist;
     __syncwarp();
 
     // search_for_one<without_lock>: levels ep.level .. 1 (hnsw.hh:341-391)
     for (uint32_t level = g.ep_level; level > 0; --level) {
-      while (greedy_step<IP, NCHUNK>(g, s_q, level, cur, closest, s_rows, s_dist, c_dist, c_vup, c_lup, lane)) {}
+      while (greedy_step<IP, NCHUNK>(g, s_q, level, cur, closest, s_rows, s_dist, c_unused, c_vup, c_lup, lane)) {}
     }
 
     // hnsw.hh:285-288 — distance recomputed (same bits), seed of the level-0 search
-    ++c_dist;
     if (lane == 0) { qd[0] = closest; qi[0] = cur; }
     uint32_t qsize = 1;
     visited_test_and_set(vis, cur, lane == 0, lane);
@@ -100,42 +125,51 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, SHN_MIN_BLOCKS) search_ke
     // search_level<without_lock>(ef, level 0) (hnsw.hh:407-476)
     uint32_t c_hot = 0, c_local = 0;
     const uint32_t l0_before = c_vl0;
-    beam_search<IP, NCHUNK>(g, s_q, 0, ef, qd, qi, qsize, s_rows, s_dist, vis, c_dist, c_vl0, c_l0, c_hot, c_local, lane);
-#ifdef SHN_COUNT_PREDICTIONS
-    t_hot += c_hot; t_local += c_local;
-#else
-    if (g.world > 1) { t_hot += c_hot; t_local += c_local; t_remote += (c_vl0 - l0_before) - c_hot - c_local; }
-#endif
+    beam_search<IP, NCHUNK, PART>(g, s_q, 0, p.ef, qd, qi, qsize, s_rows, s_dist, vis, c_unused, c_vl0, c_l0, c_hot, c_local, lane);
 
     // trim to k (:296-298); the reference reports ids in heap-array order, here ascending by distance
-    for (uint32_t j = lane; j < p.k; j += 32) {
-      const bool ok = j < qsize;
-      p.out_ids[static_cast<size_t>(q) * p.k + j] = ok ? __ldg(g.ext_id + (qi[j] & ~kExpanded)) : kInvalid;
-      if (p.out_dists) p.out_dists[static_cast<size_t>(q) * p.k + j] = ok ? qd[j] : __int_as_float(0x7f800000);
+    {
+      uint32_t* ids_out = p.out_ids;
+      float* dists_out = p.out_dists;
+      size_t out_slot = q;
+      if (p.io.in_rows) {  // routed: the result row goes to the landing buffer of the query's home GPU, at its home slot
+        uint32_t src = 0, j = q;
+        for (;;) {
+          const uint32_t c = __ldg(p.io.in_counts + src);
+          if (j < c) break;
+          j -= c; ++src;
+        }
+        out_slot = p.io.in_tags[static_cast<size_t>(src) * p.io.cap + j];
+        ids_out = p.io.out_ids[src];
+        dists_out = p.io.out_dists ? p.io.out_dists[src] : nullptr;
+      }
+      for (uint32_t j = lane; j < p.k; j += 32) {
+        const bool ok = j < qsize;
+        ids_out[out_slot * p.k + j] = ok ? __ldg(g.ext_id + (qi[j] & ~kExpanded)) : kInvalid;
+        if (dists_out) dists_out[out_slot * p.k + j] = ok ? qd[j] : __int_as_float(0x7f800000);
+      }
     }
-    const uint32_t overflowed = vis.ovf_count ? 1u : 0u;
-    if (p.per_query && lane == 0) {
-      uint32_t* o = p.per_query + static_cast<size_t>(q) * kPerQueryWords;
-      o[0] = c_dist; o[1] = c_vup; o[2] = c_vl0; o[3] = c_l0; o[4] = c_lup; o[5] = overflowed | (vis.failed ? 2u : 0u);
+    if (lane == 0) {
+      const uint32_t c_dist = c_vup + c_vl0 + 1;
+      const uint32_t overflowed = vis.ovf_count ? 1u : 0u;
+      if (p.per_query) {
+        uint32_t* o = p.per_query + static_cast<size_t>(q) * kPerQueryWords;
+        o[0] = c_dist; o[1] = c_vup; o[2] = c_vl0; o[3] = c_l0; o[4] = c_lup; o[5] = overflowed | (vis.failed ? 2u : 0u);
+      }
+      s_tot[kDistcomps] += c_dist; s_tot[kVisitedUpper] += c_vup; s_tot[kVisitedL0] += c_vl0;
+      s_tot[kListsL0] += c_l0; s_tot[kListsUpper] += c_lup; s_tot[kOverflowQueries] += overflowed;
+      s_tot[kFailedQueries] += vis.failed ? 1u : 0u;
+      s_tot[kProcessed] += 1;
+      if (PART && g.world > 1) {
+        s_tot[kRowsHot] += c_hot; s_tot[kRowsLocal] += c_local; s_tot[kRowsRemote] += (c_vl0 - l0_before) - c_hot - c_local;
+      }
     }
-    t_dist += c_dist; t_vup += c_vup; t_vl0 += c_vl0; t_l0 += c_l0; t_lup += c_lup; t_ovf += overflowed;
-    t_fail += vis.failed ? 1u : 0u;
     __syncwarp();
   }
 
   if (vis.ovf_count) visited_reset(vis, lane);  // leave the HBM table clean for the next launch
-  if (lane == 0) {
-    atomicAdd(p.totals + kDistcomps, t_dist);
-    atomicAdd(p.totals + kVisitedUpper, t_vup);
-    atomicAdd(p.totals + kVisitedL0, t_vl0);
-    atomicAdd(p.totals + kListsL0, t_l0);
-    atomicAdd(p.totals + kListsUpper, t_lup);
-    if (t_ovf) atomicAdd(p.totals + kOverflowQueries, t_ovf);
-    if (t_fail) atomicAdd(p.totals + kFailedQueries, t_fail);
-    if (t_hot) atomicAdd(p.totals + kRowsHot, t_hot);
-    if (t_local) atomicAdd(p.totals + kRowsLocal, t_local);
-    if (t_remote) atomicAdd(p.totals + kRowsRemote, t_remote);
-  }
+  __syncwarp();
+  if (lane < kNumTotals && s_tot[lane]) atomicAdd(p.totals + lane, s_tot[lane]);
 }
 
 uint32_t next_pow2(uint32_t v) {
@@ -153,26 +187,30 @@ uint32_t pick_vis_cap(uint32_t ef, uint32_t m0) {
   return cap;
 }
 
-template <bool IP, int NCHUNK>
+template <bool IP, int NCHUNK, bool PART>
 cudaError_t launch_t(const SearchParams& p, int grid, size_t smem, cudaStream_t stream) {
-  cudaError_t e = cudaFuncSetAttribute(search_kernel<IP, NCHUNK>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  cudaError_t e = cudaFuncSetAttribute(search_kernel<IP, NCHUNK, PART>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (e != cudaSuccess) return e;
-  search_kernel<IP, NCHUNK><<<grid, kWarpsPerBlock * 32, smem, stream>>>(p);
+  search_kernel<IP, NCHUNK, PART><<<grid, kWarpsPerBlock * 32, smem, stream>>>(p);
   return cudaGetLastError();
 }
 
-template <bool IP, int NCHUNK>
+template <bool IP, int NCHUNK, bool PART>
 cudaError_t occupancy_t(size_t smem, int* blocks) {
-  cudaError_t e = cudaFuncSetAttribute(search_kernel<IP, NCHUNK>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  cudaError_t e = cudaFuncSetAttribute(search_kernel<IP, NCHUNK, PART>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (e != cudaSuccess) return e;
-  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, search_kernel<IP, NCHUNK>, kWarpsPerBlock * 32, smem);
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, search_kernel<IP, NCHUNK, PART>, kWarpsPerBlock * 32, smem);
 }
 
 // dimensions the kernels are instantiated for at compile time (0 = any dim)
 int chunk_variant(uint32_t dim) { return (dim == 96 || dim == 128 || dim == 200 || dim == 960) ? static_cast<int>(dim) : 0; }
-#define DISPATCH_V(fn, ip, v, ...)                                                                   \
-  ((v) == 128 ? fn<ip, 128>(__VA_ARGS__) : (v) == 96 ? fn<ip, 96>(__VA_ARGS__) : (v) == 200 ? fn<ip, 200>(__VA_ARGS__) \
-   : (v) == 960 ? fn<ip, 960>(__VA_ARGS__) : fn<ip, 0>(__VA_ARGS__))
+#define DISPATCH_V(fn, ip, part, v, ...)                                                                                \
+  ((v) == 128 ? fn<ip, 128, part>(__VA_ARGS__) : (v) == 96 ? fn<ip, 96, part>(__VA_ARGS__)                              \
+   : (v) == 200 ? fn<ip, 200, part>(__VA_ARGS__) : (v) == 960 ? fn<ip, 960, part>(__VA_ARGS__) : fn<ip, 0, part>(__VA_ARGS__))
+// PART: the handle is a partition (rows may live on peers) or counts visits for the hot set; otherwise the plain kernel
+#define DISPATCH(fn, ip, part, v, ...)                                                                                 \
+  ((ip) ? ((part) ? DISPATCH_V(fn, true, true, v, __VA_ARGS__) : DISPATCH_V(fn, true, false, v, __VA_ARGS__))          \
+        : ((part) ? DISPATCH_V(fn, false, true, v, __VA_ARGS__) : DISPATCH_V(fn, false, false, v, __VA_ARGS__)))
 
 }  // namespace
 
@@ -180,18 +218,18 @@ cudaError_t search_plan(const DeviceGraph& g, const SearchConfig& cfg, uint32_t 
                         uint32_t* vis_cap_out) {
   const uint32_t q_floats = g.row_f4 * 4;
   const uint32_t ef_cap = (cfg.ef + 31u) & ~31u;
+  const uint32_t list_cap = g.m0 <= 32 ? 32u : 64u;
   uint32_t vis_cap = cfg.vis_cap ? next_pow2(cfg.vis_cap) : pick_vis_cap(cfg.ef, g.m0);
-  size_t bytes = kWarpsPerBlock * warp_smem_bytes(q_floats, ef_cap, vis_cap);
+  size_t bytes = kWarpsPerBlock * warp_smem_bytes(q_floats, ef_cap, list_cap, vis_cap);
   while (bytes > 200 * 1024 && vis_cap > 1024) {
     vis_cap >>= 1;
-    bytes = kWarpsPerBlock * warp_smem_bytes(q_floats, ef_cap, vis_cap);
+    bytes = kWarpsPerBlock * warp_smem_bytes(q_floats, ef_cap, list_cap, vis_cap);
   }
   if (bytes > 227 * 1024) return cudaErrorInvalidValue;
   int blocks = 0;
-  cudaError_t e;
   const int v = chunk_variant(g.dim);
-  if (cfg.ip) e = DISPATCH_V(occupancy_t, true, v, bytes, &blocks);
-  else        e = DISPATCH_V(occupancy_t, false, v, bytes, &blocks);
+  const bool part = g.world > 1 || g.visit_count != nullptr;
+  cudaError_t e = DISPATCH(occupancy_t, cfg.ip, part, v, bytes, &blocks);
   if (e != cudaSuccess) return e;
   if (blocks < 1) return cudaErrorInvalidConfiguration;
   if (cfg.warps_per_sm > 0) {
@@ -211,7 +249,7 @@ cudaError_t search_plan(const DeviceGraph& g, const SearchConfig& cfg, uint32_t 
 
 cudaError_t search_launch(const DeviceGraph& g, const SearchConfig& cfg, const float* d_queries, uint32_t nq,
                           uint32_t* d_ids, float* d_dists, uint32_t* d_per_query, SearchWorkspace& ws,
-                          cudaStream_t stream) {
+                          cudaStream_t stream, const RoutedIo* io) {
   int grid, block;
   size_t smem;
   uint32_t vis_cap;
@@ -226,7 +264,8 @@ cudaError_t search_launch(const DeviceGraph& g, const SearchConfig& cfg, const f
   p.counter = ws.counter; p.totals = ws.totals; p.ovf = ws.ovf;
   p.vis_cap = vis_cap; p.vis_limit = vis_cap / 4 * 3;
   p.ovf_cap = ws.ovf_cap; p.ovf_limit = ws.ovf_cap / 4 * 3;
-  p.q_floats = g.row_f4 * 4; p.ef_cap = (cfg.ef + 31u) & ~31u;
+  p.q_floats = g.row_f4 * 4; p.ef_cap = (cfg.ef + 31u) & ~31u; p.list_cap = g.m0 <= 32 ? 32u : 64u;
+  if (io) p.io = *io;
 
   e = cudaMemsetAsync(ws.counter, 0, sizeof(uint32_t), stream);
   if (e != cudaSuccess) return e;
@@ -234,8 +273,8 @@ cudaError_t search_launch(const DeviceGraph& g, const SearchConfig& cfg, const f
   if (e != cudaSuccess) return e;
 
   const int v = chunk_variant(g.dim);
-  if (cfg.ip) return DISPATCH_V(launch_t, true, v, p, grid, smem, stream);
-  return DISPATCH_V(launch_t, false, v, p, grid, smem, stream);
+  const bool part = g.world > 1 || g.visit_count != nullptr;
+  return DISPATCH(launch_t, cfg.ip, part, v, p, grid, smem, stream);
 }
 
 }  // namespace shn

@@ -123,7 +123,7 @@ __device__ __forceinline__ float tail_chain(float r, const float4& q, const floa
 #ifndef SHN_SMALL_PASSES
 #define SHN_SMALL_PASSES 1
 #endif
-template <bool IP, int NCHUNK, int PASSES = SHN_PASSES>
+template <bool IP, int NCHUNK, int PASSES = SHN_PASSES, bool PART = false>
 __device__ SHN_EVAL_ATTR void eval_rows(const DeviceGraph& g, const float* s_q, const uint32_t* s_rows, uint32_t cnt,
                                           float* s_out, int lane) {
   const int t = lane & 7, grp = lane >> 3;
@@ -143,7 +143,7 @@ __device__ SHN_EVAL_ATTR void eval_rows(const DeviceGraph& g, const float* s_q, 
       s[p] = 0.f;
       const uint32_t i = base + 4 * p + grp;
       const uint32_t row = s_rows[i < cnt ? i : cnt - 1];  // clamp: a redundant load instead of a divergent branch
-      rp[p] = vec_row(g, row) + t;
+      rp[p] = vec_row<PART>(g, row) + t;
     }
     const uint32_t npass = min(static_cast<uint32_t>(PASSES), (cnt - base + 3) >> 2);  // warp-uniform: passes that hold at least one row
     float4 tv[PASSES];
@@ -203,8 +203,12 @@ __device__ SHN_EVAL_ATTR void eval_rows(const DeviceGraph& g, const float* s_q, 
 // Admit the candidates (s_rows[i], s_dist[i]), i < cnt <= 64, given in stored list order, in ONE merge.
 // Equivalent to the reference's one-by-one admission (hnsw.hh:456-465) whenever no two distances are equal: the
 // running farthest distance only shrinks, so what survives is exactly the ef smallest of old and new entries;
-// old entries stay ahead of new ones at equal distance and new ones keep their list order.  s_rows / s_dist are
-// used as scratch.  Returns the lowest queue position that received a new entry (kInvalid if none).
+// old entries stay ahead of new ones at equal distance and new ones keep their list order.
+// Returns the lowest queue position that received a new entry (kInvalid if none).
+// Steps: compact the survivors (closer than the current farthest entry), rank them among themselves by counting, find
+// each one's slot among the old entries by binary search, then move the old entries at or above the lowest slot up by
+// the number of survivors ahead of them, highest block first.  (A formulation that does all the counting in one pass over
+// registers-held queue blocks was measured 4-5 % slower at every ef on B200 and removed.)
 __device__ __forceinline__ uint32_t queue_merge(float* qd, uint32_t* qi, uint32_t& qsize, uint32_t ef, uint32_t* s_rows,
                                                 float* s_dist, uint32_t cnt, int lane) {
   const bool full = qsize == ef;
@@ -362,42 +366,18 @@ __device__ __forceinline__ bool visited_test_and_set(VisitedSet& v, uint32_t id,
   return is_new;
 }
 
-// Read-only membership test against the shared table only (keys that spilled to the HBM table are reported as absent):
-// good enough to decide whether a row is worth prefetching.
-__device__ __forceinline__ bool visited_probably(const VisitedSet& v, uint32_t id) {
-  const uint32_t nbuckets = v.cap >> 2;
-  uint32_t b = hash_row(id) & (nbuckets - 1);
-  for (int probe = 0; probe < 4; ++probe) {
-    const uint4 k = reinterpret_cast<const uint4*>(v.tab)[b];
-    if (k.x == id || k.y == id || k.z == id || k.w == id) return true;
-    if (k.w == kInvalid) return false;
-    b = (b + 1) & (nbuckets - 1);
-  }
-  return false;
-}
-
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-
 // ---------------------------------------------------------------------------------------------------------------
 // ef-bounded best-first search on one level (HNSW::search_level, hnsw.hh:407-476).  On entry the queue holds the
 // seed entries (unexpanded) and the visited set holds their rows.  Level 0 reads the 2m-wide lists, upper levels the
 // m-wide ones.  Counters: distance computations / nodes visited / lists read on this level.
 // ---------------------------------------------------------------------------------------------------------------
-template <bool IP, int NCHUNK>
+template <bool IP, int NCHUNK, bool PART = false>
 __device__ __forceinline__ void beam_search(const DeviceGraph& g, const float* s_q, uint32_t level, uint32_t ef, float* qd,
                                             uint32_t* qi, uint32_t& qsize, uint32_t* s_rows, float* s_dist, VisitedSet& vis,
                                             uint32_t& c_dist, uint32_t& c_vis, uint32_t& c_lists, uint32_t& c_hot,
                                             uint32_t& c_local, int lane) {
   const uint32_t width = level == 0 ? g.m0 : g.m;
   uint32_t lb = 0;  // every entry below lb is expanded
-  // Optional (-DSHN_LIST_PREFETCH, off: no measurable gain on B200): the list of the entry most likely to be expanded
-  // NEXT (the closest unexpanded one after the current candidate; right 65 % of the time at ef = 64, 80 % at 256) is
-  // loaded while the current candidate's rows are in flight.  Purely a load-scheduling device: what is expanded, and in
-  // which order, is unchanged.
-  uint32_t pre_row = kInvalid, pre0 = kInvalid, pre1 = kInvalid;
-#ifdef SHN_COUNT_PREDICTIONS
-  uint32_t c_lists_pred = 0, c_lists_hit = 0;
-#endif
   for (;;) {
     // next_candidates.pop(): the closest entry not yet expanded
     uint32_t pos = kInvalid;
@@ -414,39 +394,12 @@ __device__ __forceinline__ void beam_search(const DeviceGraph& g, const float* s
     lb = pos + 1;
     ++c_lists;
 
-    // read_neighborlist (:437): from the registers filled during the previous expansion, or from HBM
-    uint32_t nb0, nb1 = kInvalid;
-#ifdef SHN_COUNT_PREDICTIONS
-    if (pre_row != kInvalid) ++c_lists_pred;  // diagnostic: a prediction existed
-    if (cand == pre_row) ++c_lists_hit;
-#endif
-    if (cand == pre_row) {
-      nb0 = pre0; nb1 = pre1;
-    } else {
-      const uint32_t* list = level == 0 ? l0_row(g, cand)
-                                        : g.up + (static_cast<size_t>(__ldg(g.up_base + cand)) + (level - 1)) * g.m;
-      nb0 = static_cast<uint32_t>(lane) < width ? __ldg(list + lane) : kInvalid;
-      if (width > 32) nb1 = static_cast<uint32_t>(lane) + 32 < width ? __ldg(list + lane + 32) : kInvalid;
-    }
-#ifdef SHN_LIST_PREFETCH
-    {
-      uint32_t pos2 = kInvalid;
-      for (uint32_t b = lb & ~31u; b < qsize; b += 32) {
-        const uint32_t j = b + lane;
-        const bool un = j < qsize && j >= lb && !(qi[j] & kExpanded);
-        const uint32_t mask = __ballot_sync(kFull, un);
-        if (mask) { pos2 = b + __ffs(mask) - 1; break; }
-      }
-      pre_row = kInvalid;
-      if (pos2 != kInvalid) {
-        pre_row = qi[pos2];
-        const uint32_t* list = level == 0 ? l0_row(g, pre_row)
-                                          : g.up + (static_cast<size_t>(__ldg(g.up_base + pre_row)) + (level - 1)) * g.m;
-        pre0 = static_cast<uint32_t>(lane) < width ? __ldg(list + lane) : kInvalid;
-        if (width > 32) pre1 = static_cast<uint32_t>(lane) + 32 < width ? __ldg(list + lane + 32) : kInvalid;
-      }
-    }
-#endif
+    // read_neighborlist (:437)
+    const uint32_t* list = level == 0 ? l0_row<PART>(g, cand)
+                                      : g.up + (static_cast<size_t>(__ldg(g.up_base + cand)) + (level - 1)) * g.m;
+    const uint32_t nb0 = static_cast<uint32_t>(lane) < width ? __ldg(list + lane) : kInvalid;
+    uint32_t nb1 = kInvalid;
+    if (width > 32) nb1 = static_cast<uint32_t>(lane) + 32 < width ? __ldg(list + lane + 32) : kInvalid;
 
     // the visited filter, in stored order (:440-443)
     uint32_t cnt = 0;
@@ -465,7 +418,7 @@ __device__ __forceinline__ void beam_search(const DeviceGraph& g, const float* s
     __syncwarp();
     if (cnt == 0) continue;
     c_vis += cnt; c_dist += cnt;
-    if (level == 0 && (g.world > 1 || g.visit_count)) {  // warp-uniform; never taken on the plain single-GPU path
+    if (PART && level == 0) {  // where the rows of this expansion live (and, during the warm-up pass, how often each is read)
       for (uint32_t i = lane; i < ((cnt + 31u) & ~31u); i += 32) {
         const uint32_t row = i < cnt ? s_rows[i] : 0u;
         const bool in = i < cnt;
@@ -478,37 +431,12 @@ __device__ __forceinline__ void beam_search(const DeviceGraph& g, const float* s
         c_local += __popc(__ballot_sync(kFull, mine));
       }
     }
-#ifndef SHN_ROW_PREFETCH
-    eval_rows<IP, NCHUNK>(g, s_q, s_rows, cnt, s_dist, lane);
-#else
-    // EXPERIMENT, off by default (measured slower on B200: +25 % DRAM traffic, L2 hit rate 5 % -> 39 %, but 37 % more time
-    // at ef = 64 — the extra traffic lengthens the demand-load latency more than the L2 hits shorten it).
-    // First wave of rows, then — the list of the predicted next candidate has arrived by now — pull that candidate's
-    // unvisited rows into L2 while the remaining waves and the merge run; two times out of three (ef = 64; more at
-    // larger ef) the prediction holds and the next expansion reads its rows from L2 instead of HBM.
-    const uint32_t first = min(cnt, 4u * SHN_PASSES);
-    eval_rows<IP, NCHUNK>(g, s_q, s_rows, first, s_dist, lane);
-    if (level == 0 && pre_row != kInvalid) {
-      const uint32_t lines = (g.row_f4 + 7) >> 3;
-      if (pre0 != kInvalid && pre0 < g.hot && !visited_probably(vis, pre0)) {
-        const char* rp = reinterpret_cast<const char*>(g.vec + static_cast<size_t>(pre0) * g.row_f4);
-        for (uint32_t l = 0; l < lines; ++l) prefetch_l2(rp + 128 * l);
-      }
-      if (width > 32 && pre1 != kInvalid && pre1 < g.hot && !visited_probably(vis, pre1)) {
-        const char* rp = reinterpret_cast<const char*>(g.vec + static_cast<size_t>(pre1) * g.row_f4);
-        for (uint32_t l = 0; l < lines; ++l) prefetch_l2(rp + 128 * l);
-      }
-    }
-    if (cnt > first) eval_rows<IP, NCHUNK>(g, s_q, s_rows + first, cnt - first, s_dist + first, lane);
-#endif
+    eval_rows<IP, NCHUNK, SHN_PASSES, PART>(g, s_q, s_rows, cnt, s_dist, lane);
 
     // admission against the running farthest distance (:456-465, heap.hh:34-41), all neighbours in one merge
     const uint32_t at = queue_merge(qd, qi, qsize, ef, s_rows, s_dist, cnt, lane);
     if (at < lb) lb = at;
   }
-#ifdef SHN_COUNT_PREDICTIONS
-  c_hot = c_lists_pred; c_local = c_lists_hit;  // diagnostic build only: reported as rows_hot / rows_local
-#endif
 }
 
 // One step of search_for_one (hnsw.hh:342-391) on `level`: scan the whole list of `cur`, move to the list minimum if

@@ -323,6 +323,8 @@ int main(int argc, char** argv) {
   // One full index per GPU (the build is deterministic, so the graphs are identical).  With one GPU it is searched as
   // it is; with several, every GPU keeps its share (shn_index_partition) and reads the rest from its peers — the
   // reference's memory nodes become HBM partitions, its compute-node cache the replicated hot set.
+  // one seed for every GPU's build: the graphs must be the same graph (with --seed -1 the clock is read once)
+  const uint32_t build_seed = cfg.seed == -1 ? static_cast<uint32_t>(std::time(nullptr)) : static_cast<uint32_t>(cfg.seed);
   auto make_full = [&](int gpu, bool first) -> shn_index* {
     shn_index* full = nullptr;
     if (cfg.load_index) {
@@ -330,9 +332,8 @@ int main(int argc, char** argv) {
       SHN(shn_index_load(&full, dump_paths.data(), static_cast<int>(num_servers), base.dim, cfg.m, metric, gpu));
     } else {
       if (first) status("build index");
-      const uint32_t seed = cfg.seed == -1 ? static_cast<uint32_t>(std::time(nullptr)) : static_cast<uint32_t>(cfg.seed);
       const double t0 = now_ms();
-      SHN(shn_index_build(&full, base.f.data(), nullptr, base.n, base.dim, cfg.m, cfg.ef_construction, metric, seed, gpu));
+      SHN(shn_index_build(&full, base.f.data(), nullptr, base.n, base.dim, cfg.m, cfg.ef_construction, metric, build_seed, gpu));
       if (first) {
         build_ms = now_ms() - t0;
         SHN(shn_index_build_stats(full, &bstats));
@@ -350,33 +351,31 @@ int main(int argc, char** argv) {
     return full;
   };
 
-  std::vector<shn_index*> handles(n_gpus, nullptr);
+  std::vector<shn_index*> handles(n_gpus, nullptr);  // one GPU: the index; several: the full indexes until the group holds its partitions
+  shn_group* group = nullptr;
+  double placement_kmeans_ms = 0.0, placement_fetch_ms = 0.0;
   for (int g = 0; g < n_gpus; ++g) {
     shn_index* full = make_full(cfg.gpu + g, g == 0);
-    if (n_gpus == 1) {
-      // -------- cache warm-up pass (compute_node.cc:116-131): results are discarded
-      if (cfg.use_cache && warmup.n) {
-        status("run warmup queries");
-        SHN(shn_search(full, warmup.f.data(), warmup.n, cfg.k, cfg.ef_search, ids.data(), nullptr, nullptr));
-      }
-      handles[g] = full;
-    } else {
-      if (cfg.use_cache && warmup.n) {  // the warm-up pass picks the hot set: same queries, so the same set on every GPU
-        if (g == 0) status("run warmup queries");
-        SHN(shn_index_count_visits(full, 1));
-        SHN(shn_search(full, warmup.f.data(), warmup.n, cfg.k, cfg.ef_search, ids.data(), nullptr, nullptr));
-      }
-      SHN(shn_index_partition(&handles[g], full, g, n_gpus, cfg.use_cache ? cfg.cache_ratio : 0, nullptr));
-      shn_index_free(full);
+    if (cfg.use_cache && warmup.n) {
+      // cache warm-up pass (compute_node.cc:116-131), results discarded.  Several GPUs: the pass counts visits and the
+      // most visited nodes join the replicated hot set — same queries on every GPU, so the same set everywhere
+      if (g == 0) status("run warmup queries");
+      if (n_gpus > 1) SHN(shn_index_count_visits(full, 1));
+      SHN(shn_search(full, warmup.f.data(), warmup.n, cfg.k, cfg.ef_search, ids.data(), nullptr, nullptr));
     }
-    hbm_bytes += shn_index_hbm_bytes(handles[g]);
+    handles[g] = full;
   }
-  if (n_gpus > 1) {
-    for (int g = 0; g < n_gpus; ++g) {
-      uint64_t raw[2];
-      SHN(shn_index_partition_export(handles[g], nullptr, nullptr, raw));
-      for (int o = 0; o < n_gpus; ++o) if (o != g) SHN(shn_index_partition_attach(handles[o], g, nullptr, nullptr, raw));
-    }
+  if (n_gpus == 1) {
+    hbm_bytes = shn_index_hbm_bytes(handles[0]);
+  } else {
+    // memory nodes -> HBM partitions (NVLink peer reads), compute-node cache -> replicated hot set; with --routing the
+    // nodes are placed by k-means cluster and the queries run on the GPU of their nearest centroid (compute_node.cc:110-131,
+    // query_router.hh:280-387)
+    SHN(shn_group_create(&group, handles.data(), n_gpus, cfg.use_cache ? cfg.cache_ratio : 0, cfg.routing ? 1 : 0, cfg.routing ? 1 : 0,
+                         0.25, std::max<uint64_t>(1, queries.n), cfg.k, 1234));
+    for (int g = 0; g < n_gpus; ++g) { shn_index_free(handles[g]); handles[g] = nullptr; }
+    for (int g = 0; g < n_gpus; ++g) hbm_bytes += shn_index_hbm_bytes(shn_group_partition(group, g));
+    SHN(shn_group_timings(group, &placement_kmeans_ms, &placement_fetch_ms));
   }
   out["allocated_local_buffer_size"] = hbm_bytes;
   out["actual_total_local_buffer_size"] = hbm_bytes;
@@ -393,31 +392,13 @@ int main(int argc, char** argv) {
   std::memset(&st, 0, sizeof st);
   std::vector<shn_stats> per_gpu(n_gpus);
   const double q0 = now_ms();
+  double routing_ms = 0.0;
   if (n_gpus == 1) {
     SHN(shn_search(handles[0], queries.f.data(), queries.n, cfg.k, cfg.ef_search, ids.data(), nullptr, &st));
     per_gpu[0] = st;
   } else {
-    std::vector<std::string> errors(n_gpus);
-    std::vector<std::thread> workers;
-    for (int g = 0; g < n_gpus; ++g) {
-      workers.emplace_back([&, g] {
-        std::vector<float> shard;
-        std::vector<uint32_t> slots;
-        for (uint32_t q = g; q < queries.n; q += n_gpus) {
-          slots.push_back(q);
-          shard.insert(shard.end(), queries.f.begin() + static_cast<size_t>(q) * queries.dim, queries.f.begin() + static_cast<size_t>(q + 1) * queries.dim);
-        }
-        std::vector<uint32_t> res(slots.size() * cfg.k);
-        if (shn_search(handles[g], shard.data(), slots.size(), cfg.k, cfg.ef_search, res.data(), nullptr, &per_gpu[g]) != SHN_OK) {
-          errors[g] = shn_last_error();
-          return;
-        }
-        for (size_t i = 0; i < slots.size(); ++i)
-          std::memcpy(ids.data() + static_cast<size_t>(slots[i]) * cfg.k, res.data() + i * cfg.k, cfg.k * sizeof(uint32_t));
-      });
-    }
-    for (auto& w : workers) w.join();
-    for (int g = 0; g < n_gpus; ++g) if (!errors[g].empty()) die("shn_search on GPU " + std::to_string(cfg.gpu + g) + ": " + errors[g]);
+    // GPU g takes the queries with id % gpus == g (io/read_data.hh:58); the fan-out lives behind the C ABI (csrc/group.cu)
+    SHN(shn_group_search(group, queries.f.data(), queries.n, cfg.k, cfg.ef_search, ids.data(), nullptr, per_gpu.data(), &routing_ms));
     for (int g = 0; g < n_gpus; ++g) {
       const shn_stats& p = per_gpu[g];
       st.distcomps += p.distcomps; st.visited_nodes += p.visited_nodes; st.visited_nodes_l0 += p.visited_nodes_l0;
@@ -511,14 +492,15 @@ int main(int argc, char** argv) {
   for (int g = 1; g < n_gpus; ++g) { tj["build_c" + std::to_string(g)] = build_ms; tj["query_c" + std::to_string(g)] = query_ms; }
   tj["build_max"] = build_ms;
   tj["query_max"] = query_ms;
-  tj["placement_fetch"] = 0.0;
-  tj["placement_kmeans"] = 0.0;
-  tj["routing"] = 0.0;
+  tj["placement_fetch"] = placement_fetch_ms;    // several GPUs: splitting the index into the GPUs' shares
+  tj["placement_kmeans"] = placement_kmeans_ms;  // --routing: k-means over the upper-level nodes + balanced assignment
+  tj["routing"] = routing_ms;                    // --routing: route + deliver the batch (slowest GPU)
   if (cfg.use_cache) tj["warmup_routing"] = 0.0;
 
   std::cerr << std::endl << "statistics:" << std::endl;
   out.dump(std::cout, 0);
   std::cout << std::endl;
+  shn_group_free(group);
   for (shn_index* h : handles) shn_index_free(h);
   return 0;
 }

@@ -79,6 +79,16 @@ def lib():
         L.shn_route_queries.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_int, C.c_void_p, C.c_uint64, C.c_double, C.c_void_p, C.c_int]
         L.shn_index_partition_export.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.shn_index_partition_attach.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.shn_router_create.argtypes = [C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p, C.c_double, C.c_uint64, C.c_uint32]
+        L.shn_router_free.argtypes = [C.c_void_p]
+        L.shn_router_free.restype = None
+        L.shn_router_export.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.shn_router_attach.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_uint64]
+        L.shn_router_scatter.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
+        L.shn_router_search.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.POINTER(Stats)]
+        L.shn_router_results.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+        L.shn_router_counts.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.shn_router_destinations.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
         L.shn_draw_levels.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p]
         L.shn_set_build_option.argtypes = [C.c_char_p, C.c_int64]
         L.shn_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int64]
@@ -251,6 +261,68 @@ class Index:
         _check(lib().shn_search_device(self._h, d_queries, nq, k, ef, d_ids, d_dists or None, d_counters or None,
                                        stream or None, C.byref(st) if want_stats else None))
         return st.as_dict() if want_stats else None
+
+
+class _DevicePointer:
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = dict(shape=tuple(shape), typestr=typestr, data=(int(ptr), False), version=2)
+
+
+def device_view(ptr, shape, typestr):
+    """A torch tensor aliasing device memory owned by the library (e.g. a router's landing buffers): '<i4', '<f4', '|u1'."""
+    import torch
+    return torch.as_tensor(_DevicePointer(ptr, shape, typestr), device="cuda")
+
+
+class Router:
+    """Query routing fused with the exchange (include/shn.h shn_router_*): scatter -> barrier -> search -> barrier."""
+
+    def __init__(self, index, centroids, slack=0.25, max_batch=1 << 20, k_max=10):
+        c = np.ascontiguousarray(centroids, dtype=np.float32)
+        self._h = C.c_void_p()
+        self.index, self.world = index, c.shape[0]
+        _check(lib().shn_router_create(C.byref(self._h), index._h, c.ctypes.data, slack, max_batch, k_max))
+
+    def export(self, want_fd=False):
+        """(fd or None, size, raw device pointer) of this rank's exchange block."""
+        fd, size, raw = C.c_int(-1), C.c_uint64(), C.c_uint64()
+        _check(lib().shn_router_export(self._h, C.byref(fd) if want_fd else None, C.byref(size), C.byref(raw)))
+        return (int(fd.value) if want_fd else None), int(size.value), int(raw.value)
+
+    def attach(self, peer, fd=-1, size=0, raw_ptr=0):
+        _check(lib().shn_router_attach(self._h, peer, fd, size, raw_ptr))
+
+    def scatter(self, d_queries, nq, stream=0):
+        _check(lib().shn_router_scatter(self._h, d_queries, nq, stream or None))
+
+    def search(self, k, ef, stream=0, want_stats=True):
+        st = Stats()
+        _check(lib().shn_router_search(self._h, k, ef, stream or None, C.byref(st) if want_stats else None))
+        return st.as_dict() if want_stats else None
+
+    def results(self):
+        """Raw device pointers (ids, dists) of this rank's landing buffers."""
+        i, d = C.c_void_p(), C.c_void_p()
+        _check(lib().shn_router_results(self._h, C.byref(i), C.byref(d)))
+        return int(i.value), int(d.value)
+
+    def counts(self, stream=0):
+        sent = np.zeros(self.world, np.uint32)
+        recv = np.zeros(self.world, np.uint32)
+        _check(lib().shn_router_counts(self._h, sent.ctypes.data, recv.ctypes.data, stream or None))
+        return sent, recv
+
+    def destinations(self):
+        p = C.c_void_p()
+        _check(lib().shn_router_destinations(self._h, C.byref(p)))
+        return int(p.value)
+
+    def close(self):
+        if getattr(self, "_h", None) and _LIB is not None:
+            _LIB.shn_router_free(self._h)
+            self._h = None
+
+    __del__ = close
 
 
 def repartition_dumps(dumps, dim, m, n_parts_out):

@@ -83,7 +83,7 @@ int shn_index_build_device(shn_index** out, const float* d_base, const uint32_t*
  * never more than one above the current top (:106).  Identical to a single-coroutine build of the reference. */
 int shn_draw_levels(uint64_t n, uint32_t m, uint32_t seed, uint32_t* levels);
 /* Construction knobs, process-wide, read when shn_index_build* starts: "batch_max" (nodes inserted per step, default
- * 16384) and "batch_div" (a step inserts at most 1/batch_div of the current graph, default 32); 0 = default. */
+ * 16384) and "batch_div" (a step inserts at most 1/batch_div of the current graph, default 64); 0 = default. */
 int shn_set_build_option(const char* key, int64_t value);
 /* Build-time counters (distcomps, processed, kernel_ms) of a handle created by shn_index_build*. */
 int shn_index_build_stats(const shn_index*, shn_stats* out);
@@ -126,7 +126,9 @@ int shn_set_option(shn_index*, const char* key, int64_t value);
  *   - 1/world of the remaining rows (round-robin);
  * the other shares are read over NVLink through peer-mapped pointers.  Results do not depend on the partitioning. */
 int shn_index_count_visits(shn_index*, int enable);   /* on: allocate + zero the per-node counters; searches then count */
-/* copy the counters to (write_back = 0) or from (write_back = 1) a device buffer of n u32 — the caller all-reduces */
+/* copy the counters to (write_back = 0) or from (write_back = 1) a device buffer of n u32 — the caller all-reduces.
+ * Complete on return; with write_back the caller's writes to d_counts must have completed (the call waits for no stream
+ * but the handle's own). */
 int shn_index_visit_counts(shn_index*, uint32_t* d_counts, int write_back);
 /* d_owner == NULL: cold rows dealt round-robin (the reference's uniform scatter).  d_owner = device array of n bytes,
  * owner[row] < world (from shn_placement_fit): rank p keeps exactly the cold rows it owns. */
@@ -150,6 +152,59 @@ int shn_index_partition_export(const shn_index*, int* fds /*2*/, uint64_t* sizes
  * Searching needs every peer attached. */
 int shn_index_partition_attach(shn_index*, int peer, const int* fds, const uint64_t* sizes, const uint64_t* raw_ptrs);
 
+/* ---- query routing between the GPUs of a partitioned index, fused with the exchange (csrc/router.cu) ---------------
+ * The reference: QueryRouter (src/router/query_router.hh:280-387) sends a query to the compute node of its nearest
+ * k-means centroid (src/cache/placement.hh:22-106) unless that node is over its per-batch limit (:356-368, limits
+ * :106-151); queries are relayed with SEND/RECV through a memory node (:83-104,195-210).  Here every GPU owns one
+ * exchange block (inbox + landing buffers) that all peers map; a routed batch is
+ *     every rank: shn_router_scatter  -> barrier -> shn_router_search -> barrier -> results in shn_router_results
+ * scatter routes on the GPU (no host loop, nothing copied to the host) and stores each query straight into the inbox
+ * of its destination over NVLink; search writes each result row straight into the landing buffer of the query's home
+ * GPU.  The barriers are the caller's (a stream-ordered collective between processes, events between the streams of
+ * one process).  world == 1 handles work too (everything stays local).
+ * centroids: host [world][dim] from shn_placement_fit.  slack: a rank takes at most (1 + slack) * nq / world + 1
+ * queries of a batch.  max_batch / k_max size the exchange block and must be the same on every rank. */
+typedef struct shn_router shn_router;
+int shn_router_create(shn_router** out, shn_index* partition, const float* centroids, double slack, uint64_t max_batch,
+                      uint32_t k_max);
+void shn_router_free(shn_router*);
+/* The exchange block as a POSIX fd (CUDA VMM export; the caller passes it to the other processes and closes it), its
+ * mapped size, and the raw device pointer (for peers inside the same process).  Any output may be NULL. */
+int shn_router_export(const shn_router*, int* fd, uint64_t* size, uint64_t* raw_ptr);
+/* Attach rank `peer`'s block: raw_ptr != 0 (same process) or fd + size (received from another process). */
+int shn_router_attach(shn_router*, int peer, int fd, uint64_t size, uint64_t raw_ptr);
+/* Route d_queries[nq][dim] (device memory of this GPU) and deliver them.  Asynchronous on `stream` (NULL = the router's). */
+int shn_router_scatter(shn_router*, const float* d_queries, uint64_t nq, void* stream);
+/* Search what arrived (HNSW::knn per query, as shn_search_device) and deliver the results.  Asynchronous unless stats. */
+int shn_router_search(shn_router*, uint32_t k, uint32_t ef, void* stream, shn_stats* stats);
+/* This rank's landing buffers: row q = results of the q-th query it scattered (row stride = k of the search). */
+int shn_router_results(const shn_router*, uint32_t** d_ids, float** d_dists);
+/* Host copies of how many queries the last scatter sent to each rank / the inbox holds from each rank (synchronises). */
+int shn_router_counts(shn_router*, uint32_t* sent /*[world]*/, uint32_t* received /*[world]*/, void* stream);
+/* dest[q] of the last scatter (device pointer, one byte per query). */
+int shn_router_destinations(const shn_router*, const uint8_t** d_dest);
+
+/* ---- one process, several GPUs: the whole multi-GPU fan-out behind one handle (csrc/group.cu) ----------------------
+ * Replaces what ComputeNode does around the hot path with >1 compute node: placement + warm-up (src/compute_node.cc:
+ * 110-131), the round-robin query split (src/io/read_data.hh:58) and the routed query phase (:191-245).
+ * full[g]: one full index per GPU, the SAME graph on every GPU (built with the same seed or loaded from the same dumps;
+ * checked).  If the caller ran warm-up queries with shn_index_count_visits on them (the same queries on every GPU), the
+ * most visited nodes join the replicated hot set.  The group takes over nothing: the caller frees full[g] afterwards.
+ * placement_by_cluster: nodes stored on the GPU of their nearest k-means centroid (shn_placement_fit) instead of dealt
+ * round-robin; routing (needs placement_by_cluster): queries run on the GPU of their nearest centroid (shn_router_*). */
+typedef struct shn_group shn_group;
+int shn_group_create(shn_group** out, shn_index* const* full, int n_gpus, uint32_t cache_ratio_pct, int placement_by_cluster,
+                     int routing, double slack, uint64_t max_batch, uint32_t k_max, uint32_t seed);
+void shn_group_free(shn_group*);
+int shn_group_size(const shn_group*);
+shn_index* shn_group_partition(shn_group*, int i); /* GPU i's partition handle (introspection; owned by the group) */
+int shn_group_timings(const shn_group*, double* placement_kmeans_ms, double* placement_partition_ms);
+/* HNSW::knn for nq host queries, dealt to the GPUs by query id % n_gpus; results in query order (as shn_search).
+ * per_gpu (may be NULL): n_gpus shn_stats, `processed` = queries that GPU answered; routing_ms (may be NULL): the
+ * slowest GPU's route + scatter time. */
+int shn_group_search(shn_group*, const float* queries, uint64_t nq, uint32_t k, uint32_t ef, uint32_t* out_ids,
+                     float* out_dists, shn_stats* per_gpu, double* routing_ms);
+
 /* ---- search ------------------------------------------------------------------------------------------------ */
 
 /* k-NN for nq queries: HNSW::knn (hnsw/hnsw.hh:253-307) for every slot that hnsw::schedule<D,false>
@@ -163,7 +218,10 @@ int shn_search(shn_index*, const float* queries, uint64_t nq, uint32_t k, uint32
 
 /* Same with every buffer resident in the HBM of the index's GPU; `stream` is a cudaStream_t (NULL = the
  * handle's own stream).  Asynchronous unless stats != NULL.  per_query_counters (device, may be NULL) receives 6
- * u32 per query: distcomps, visited_nodes, visited_nodes_l0, lists_l0, lists_upper, overflow flag. */
+ * u32 per query: distcomps, visited_nodes, visited_nodes_l0, lists_l0, lists_upper, flags (bit 0: the visited set
+ * spilled to HBM, still exact; bit 1: it overflowed — that row of the output is invalid).  With stats == NULL that flag
+ * is the only report of SHN_ERR_CAPACITY.  One launch per handle is in flight at a time: a call on another stream first
+ * waits (on the device) for the handle's previous launch. */
 int shn_search_device(shn_index*, const float* d_queries, uint64_t nq, uint32_t k, uint32_t ef, uint32_t* d_out_ids,
                       float* d_out_dists, uint32_t* d_per_query_counters, void* stream, shn_stats* stats);
 

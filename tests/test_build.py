@@ -138,10 +138,8 @@ def test_sequential_limit_reproduces_the_reference_graph(pkg, n, dim, m, efc, ip
     """With one node per batch the GPU construction kernels execute the reference's sequential insert: every neighbour
     list must then hold the same SET of nodes as the reference's graph (orc_build = the reference's single-coroutine
     build, pinned in test_oracle_pin.py); only the order inside a list differs (heap-array order vs ascending).
-    Opt-in (SHN_TEST_SEQUENTIAL_BUILD=1): written after the GPU budget of round 1 was spent, not yet run on hardware."""
-    import os
-    if os.environ.get("SHN_TEST_SEQUENTIAL_BUILD") != "1":
-        pytest.skip("opt-in: SHN_TEST_SEQUENTIAL_BUILD=1")
+    This pins the builder's kernels (descent, efC beam search, selection heuristic, back-link shrink) to the reference's
+    HNSW::insert end to end; the batched build differs from it only in what a node can see of its own batch."""
     base, _ = datagen.base_and_queries(n, 1, dim, normalize=ip)
     want_dump, _ = hnsw_oracle.build(base, m=m, efc=efc, seed=1234, ip=ip)
     want = hnsw_oracle.Index([want_dump], dim, m)

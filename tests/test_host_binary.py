@@ -129,9 +129,8 @@ def test_two_gpus_one_partitioned_index(tmp_path):
     """--gpus 2: memory nodes become HBM partitions (in-process peer pointers), the warm-up pass picks the hot set; the
     answers must be those of the single-GPU run, and the cache keys of the JSON now carry real hit/miss counts."""
     import torch
-    if torch.cuda.device_count() < 2 or os.environ.get("SHN_TEST_MULTI_GPU") != "1":
-        pytest.skip("needs two GPUs and SHN_TEST_MULTI_GPU=1 (see DESIGN.md: the in-process cross-device path of "
-                    "shine_b200 --gpus N was fixed after its last run on hardware and is not re-validated yet)")
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
     n, nq, dim, m, efc, k, ef = 8000, 400, 32, 16, 100, 10, 64
     base, queries = datagen.base_and_queries(n, nq + 200, dim)
     data = tmp_path / "synth-8k"
@@ -154,3 +153,14 @@ def test_two_gpus_one_partitioned_index(tmp_path):
     c = d2["cache"]
     assert c["hits_total"] > 0 and c["misses_total"] > 0 and 0.5 < c["hit_rate"] < 1.0
     assert set(c["local_hit_rates"]) == {"c0", "c1"} and c["cache_size_ratio"] == 10
+    assert d2["timings"]["placement_fetch"] > 0 and d2["timings"]["routing"] == 0.0
+    # --routing (compute_node.cc:191-245): nodes placed by k-means cluster, queries answered by the GPU of their nearest
+    # centroid; same answers, fewer remote reads, real timings in the reference's keys
+    three = run(*common, "--load-index", "--gpus", "2", "--cache", "--cache-ratio", "10", "--routing")
+    assert three.returncode == 0, three.stderr
+    d3 = json.loads(three.stdout)
+    assert d3["queries"]["recall"] == d1["queries"]["recall"]
+    assert d3["queries"]["dist_comps"] == d1["queries"]["dist_comps"]
+    assert d3["queries"]["processed_local"]["c0"] + d3["queries"]["processed_local"]["c1"] == nq
+    assert d3["timings"]["placement_kmeans"] > 0 and d3["timings"]["routing"] > 0
+    assert d3["cache"]["misses_total"] < c["misses_total"], "routing must cut the remote reads"

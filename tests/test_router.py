@@ -1,0 +1,139 @@
+"""GPU-side query router fused with the exchange (csrc/router.cu, include/shn.h shn_router_*).  The ranks of a
+partitioned index are emulated on one device (raw-pointer attach), the barriers between the phases are stream
+synchronisations.  Checked: the routing rule against a host replay of query_router.hh:356-368, the inbox counts, and
+that every result row lands at its home slot bit-identical to an unrouted search of the full index."""
+import numpy as np
+import pytest
+
+import datagen
+
+pytestmark = pytest.mark.gpu
+
+
+def replay_router(dist, limit):
+    """query_router.hh:356-368 in query order: nearest centroid whose rank is under `limit`; else the farthest."""
+    nq, world = dist.shape
+    order = np.argsort(dist, axis=1, kind="stable")
+    hist = np.zeros(world, np.int64)
+    dest = np.empty(nq, np.uint8)
+    slot = np.empty(nq, np.uint32)
+    for q in range(nq):
+        pick = next((c for c in order[q] if hist[c] < limit), order[q][-1])
+        dest[q] = pick
+        slot[q] = hist[pick]
+        hist[pick] += 1
+    return dest, slot, hist
+
+
+def centroid_dist(q, cent, ip):
+    q64, c64 = q.astype(np.float64), cent.astype(np.float64)
+    if ip:
+        return -(q64 @ c64.T)
+    return ((q64[:, None, :] - c64[None, :, :]) ** 2).sum(2)
+
+
+def make_group(pkg, full, world, owner_ptr, cent, nq_max, slack, ratio=5):
+    import torch
+    parts = [full.partition(r, world, ratio, d_owner=owner_ptr) for r in range(world)]
+    ex = [p.partition_export() for p in parts]
+    for r, p in enumerate(parts):
+        for peer in range(world):
+            if peer != r:
+                p.partition_attach(peer, raw_ptrs=ex[peer][2])
+    routers = [pkg.Router(p, cent, slack=slack, max_batch=nq_max, k_max=10) for p in parts]
+    rex = [r.export() for r in routers]
+    for r, rt in enumerate(routers):
+        for peer in range(world):
+            if peer != r:
+                rt.attach(peer, raw_ptr=rex[peer][2])
+    torch.cuda.synchronize()
+    return parts, routers
+
+
+@pytest.mark.parametrize("world,ip,slack,skew", [(4, False, 0.25, False), (2, True, 0.25, False), (4, False, 0.0, True),
+                                                 (8, False, 0.1, True), (3, False, 0.25, False)])
+def test_routed_step_matches_unrouted_search(pkg, world, ip, slack, skew):
+    import torch
+    n, dim, nq = 30000, 32, 3000
+    base, queries = datagen.base_and_queries(n, world * nq, dim, normalize=ip)
+    if skew:  # most queries prefer the same rank: the per-batch limits bind and the slow path of the assignment runs
+        queries[: world * nq * 3 // 4] = base[: world * nq * 3 // 4] * 0.05 + queries[0] * 0.95
+    with pkg.Index.build(base, 16, 100, ip=ip) as full:
+        ref_ids, ref_d, _ = full.search(queries, 10, 64)
+        owner = torch.empty(n, dtype=torch.uint8, device="cuda")
+        cent, _ = full.placement_fit(world, owner.data_ptr(), slack=0.05)
+        parts, routers = make_group(pkg, full, world, owner.data_ptr(), cent, nq, slack)
+    try:
+        q_dev = [torch.from_numpy(queries[r * nq:(r + 1) * nq]).cuda() for r in range(world)]
+        sent = np.zeros((world, world), np.int64)
+        dests = []
+        for r, rt in enumerate(routers):                       # phase 1+2 on every rank
+            rt.scatter(q_dev[r].data_ptr(), nq)
+        torch.cuda.synchronize()                                # barrier
+        limit = int((1.0 + slack) * nq / world + 1.0)
+        for r, rt in enumerate(routers):
+            s, _ = rt.counts()
+            sent[r] = s
+            d_host = pkg.device_view(rt.destinations(), (nq,), "|u1").cpu().numpy()
+            dests.append(d_host)
+            assert s.sum() == nq and s.max() <= limit
+            # the rule, replayed on the host (float64 distances; queries whose two nearest centroids are within 1e-5 may flip)
+            dist = centroid_dist(queries[r * nq:(r + 1) * nq], cent, ip)
+            want, _, hist = replay_router(dist, limit)
+            srt = np.sort(dist, axis=1)
+            ambiguous = (np.abs(srt[:, 1] - srt[:, 0]) <= 1e-5 * np.maximum(1.0, np.abs(srt[:, 0]))).any() if world > 1 else False
+            agree = (want == d_host).mean()
+            if not ambiguous:
+                assert agree == 1.0 and (hist == s).all(), f"rank {r}: routing differs from the sequential rule ({agree:.4f})"
+            else:
+                assert agree > 0.98
+        received = np.zeros((world, world), np.int64)
+        for r, rt in enumerate(routers):
+            _, rc = rt.counts()
+            received[r] = rc
+        assert (received == sent.T).all()
+        tot_remote = tot = 0
+        for r, rt in enumerate(routers):                       # phase 3 on every rank
+            st = rt.search(10, 64)
+            assert st["processed"] == received[r].sum()
+            tot_remote += st["rows_remote"]; tot += st["rows_hot"] + st["rows_local"] + st["rows_remote"]
+        torch.cuda.synchronize()                                # barrier
+        for r, rt in enumerate(routers):
+            p_ids, p_d = rt.results()
+            got_i = pkg.device_view(p_ids, (nq, 10), "<i4").cpu().numpy().view(np.uint32)
+            got_d = pkg.device_view(p_d, (nq, 10), "<f4").cpu().numpy()
+            sl = slice(r * nq, (r + 1) * nq)
+            assert (got_i == ref_ids[sl]).all(), f"rank {r}: ids differ from the unrouted search"
+            assert (got_d.view(np.uint32) == ref_d[sl].view(np.uint32)).all()
+        print(f"world {world}: remote share of level-0 reads {tot_remote / max(1, tot):.3f}, sent matrix\n{sent}")
+    finally:
+        for rt in routers:
+            rt.close()
+        for p in parts:
+            p.close()
+
+
+def test_router_on_a_single_gpu_index_and_errors(pkg):
+    import torch
+    base, queries = datagen.base_and_queries(5000, 700, 24)
+    with pkg.Index.build(base, 8, 60) as ix:
+        ref_ids, ref_d, _ = ix.search(queries, 5, 40)
+        cent = base[:1].copy()
+        rt = pkg.Router(ix, cent, slack=0.25, max_batch=1000, k_max=8)
+        q = torch.from_numpy(queries).cuda()
+        for _ in range(2):  # the exchange block is reusable
+            rt.scatter(q.data_ptr(), len(queries))
+            st = rt.search(5, 40)
+            assert st["processed"] == len(queries)
+            p_ids, _ = rt.results()
+            ids = pkg.device_view(p_ids, (len(queries), 5), "<i4").cpu().numpy().view(np.uint32)
+            assert (ids == ref_ids).all()
+        with pytest.raises(pkg.ShnError):
+            rt.scatter(q.data_ptr(), 1001)        # larger than max_batch
+        with pytest.raises(pkg.ShnError):
+            rt.search(9, 40)                      # k above k_max
+        with pytest.raises(pkg.ShnError):
+            rt.attach(0, raw_ptr=1)
+        rt.scatter(q.data_ptr(), 0)               # an empty batch is fine
+        assert rt.search(5, 40)["processed"] == 0
+        rt.close()

@@ -173,3 +173,35 @@ def test_live_parity_against_reference_built_index(pkg, m, dim, ip, n):
             if (ct["tie"] == 0).all():
                 assert st["distcomps"] == int(ct["distcomps"].sum())
                 assert st["lists_l0"] == int(ct["lists_l0"].sum()) and st["lists_upper"] == int(ct["lists_upper"].sum())
+
+
+def test_c1_sift1m_reference_built_id_parity(pkg):
+    """SURVEY 8d C1 at its stated size: 1 M x 128 fp32, L2, M=16, efC=200, the index built by the REFERENCE's own insert
+    path (all host threads, a few minutes), ef=64, k=10: the GPU's ids against the pinned oracle on the same dump.
+    Opt-out only (SHN_SKIP_C1=1)."""
+    import os
+    import shine_ref
+    import datagen
+    if os.environ.get("SHN_SKIP_C1") == "1":
+        pytest.skip("SHN_SKIP_C1=1")
+    if not shine_ref.available():
+        pytest.skip("oracle/_ref not built")
+    n = int(os.environ.get("SHN_C1_ROWS", 1_000_000))
+    base, queries = datagen.base_and_queries(n, 10_000, 128)
+    threads = os.cpu_count() or 4
+    dumps, _, secs = shine_ref.build(base, m=16, efc=200, threads=threads, coroutines=4, seed=1234)
+    print(f"reference build of {n} rows on {threads} threads: {secs:.0f}s")
+    oracle = hnsw_oracle.Index(dumps, 128, 16)
+    with pkg.Index.from_dumps(dumps, 128, 16) as ix:
+        ids, dists, st = ix.search(queries, 10, 64)
+    oi, od, _, ct = oracle.knn(queries, 10, 64, counters=True, track_ties=True, threads=threads)
+    n_clean = compare(ids, dists, oi, od, ct["tie"])
+    gi, _ = canon(ids, dists)
+    ri, _ = canon(oi, od)
+    same = (gi == ri).all(axis=1).mean()
+    print(f"C1: {n_clean} of {len(ids)} queries tie-free and bit-identical; identical id lists overall: {same:.5f}")
+    assert n_clean >= 0.9 * len(ids) and same >= 0.999
+    if (ct["tie"] == 0).all():
+        assert st["distcomps"] == int(ct["distcomps"].sum())
+    gt, _ = pkg.bruteforce_topk(base, queries[:1000], 10)   # exact ground truth on the GPU (csrc/bruteforce*.cu)
+    assert datagen.recall(ids[:1000], gt) > 0.9
