@@ -255,18 +255,22 @@ def partitioned_block(pkg, args, dist, rank, world, dev, local_rank, peak):
     torch.cuda.empty_cache()
     efs = [args.part_ef] if args.part_ef else [100]
     sweep = []
-    for ef in sorted(set(efs + [64])):
-        st = ix.search_device(batches[0].data_ptr(), nq, K, ef, ids.data_ptr(), dists.data_ptr(), stream=stream)
-        sweep.append(dict(ef=ef, recall=round(recall_at_k(ids[:nrec], gt), 4), whole_index_qps_per_gpu=round(nq / st["kernel_ms"] * 1e3, 1),
+    ef = efs[0]
+    whole_ids = None  # the whole-index answers for batch 0 at the block's ef: what the partitioned index must return too
+    for e in sorted(set(efs + [64])):
+        st = ix.search_device(batches[0].data_ptr(), nq, K, e, ids.data_ptr(), dists.data_ptr(), stream=stream)
+        sweep.append(dict(ef=e, recall=round(recall_at_k(ids[:nrec], gt), 4), whole_index_qps_per_gpu=round(nq / st["kernel_ms"] * 1e3, 1),
                           alg_bytes_per_query=round(st["algorithmic_bytes"] / nq, 1)))
         log(f"[rank {rank}] whole index on one GPU: {sweep[-1]}")
-    ef = efs[0]
+        if e == ef:
+            whole_ids = ids.clone()
     whole = next(s for s in sweep if s["ef"] == ef)
 
     # warm-up pass with visit counting (compute_node.cc:116-131) -> the same hot set on every rank
     t0 = time.time()
     warm = synth_rows(min(nq, 200_000), wl["dim"], 7007 + rank, dev, wl["normalize"])
     ix.count_visits(True)
+    torch.cuda.synchronize()
     ix.search_device(warm.data_ptr(), warm.shape[0], K, ef, ids.data_ptr(), stream=stream)
     counts = torch.empty(ix.n, dtype=torch.int32, device=dev)
     ix.visit_counts(counts.data_ptr())
@@ -290,15 +294,43 @@ def partitioned_block(pkg, args, dist, rank, world, dev, local_rank, peak):
     os.close(fd)
     dist.barrier()
     setup_s = time.time() - t0
-    log(f"[rank {rank}] partitioned x{world}: part sizes {sizes.tolist()}, hbm {part.hbm_bytes / 1e9:.1f} GB, setup {setup_s:.1f}s (k-means fit {t_fit:.1f}s)")
-    p_ids, p_d = router.results()
-    land_i = pkg.device_view(p_ids, (nq, K), "<i4")
-    land_d = pkg.device_view(p_d, (nq, K), "<f4")
     token = torch.zeros(1, dtype=torch.int32, device=dev)
 
     def fence():  # stream-ordered barrier between the ranks: every peer's preceding kernels have completed
         dist.all_reduce(token)
 
+    # halo: a routed warm-up pass with visit counting, then every GPU caches the peer-owned rows it read most
+    halo_rows = 0
+    if args.halo_ratio:
+        t_h = time.time()
+        part.count_visits(True)
+        warm2 = synth_rows(min(nq, 200_000), wl["dim"], 9009 + rank, dev, wl["normalize"])
+        torch.cuda.synchronize(); dist.barrier()
+        router.scatter(warm2.data_ptr(), warm2.shape[0], stream=stream)
+        fence()
+        router.search(K, ef, stream=stream, want_stats=False)
+        fence()
+        torch.cuda.synchronize(); dist.barrier()
+        halo_rows = part.build_halo(args.halo_ratio)
+        dist.barrier()
+        log(f"[rank {rank}] halo: {halo_rows} rows ({100.0 * halo_rows / wl['n']:.2f}% of the nodes) in {time.time() - t_h:.1f}s")
+        del warm2
+    setup_s = time.time() - t0
+    log(f"[rank {rank}] partitioned x{world}: part sizes {sizes.tolist()}, hbm {part.hbm_bytes / 1e9:.1f} GB, setup {setup_s:.1f}s (k-means fit {t_fit:.1f}s)")
+    # every rank must have cut the same graph the same way (a share is addressed with the reader's numbering)
+    p_hot, _, p_ep = part.partition_info()
+    sig = torch.tensor([p_hot, p_ep] + [int(x) for x in sizes], dtype=torch.int64, device=dev)
+    sigs = [torch.zeros_like(sig) for _ in range(world)]
+    dist.all_gather(sigs, sig)
+    if any(not torch.equal(sigs[0], x) for x in sigs):
+        raise SystemExit(f"[rank {rank}] the ranks partitioned different graphs: {[x.tolist() for x in sigs]}")
+    # parity of the partitioned index before anything is timed: the unrouted search of this rank's partition (hot set + own
+    # share + NVLink peer reads) must return what the whole index returned
+    part.search_device(batches[0].data_ptr(), nq, K, ef, ids.data_ptr(), stream=stream)
+    part_identical = float((ids == whole_ids).all(1).float().mean())
+    p_ids, p_d = router.results()
+    land_i = pkg.device_view(p_ids, (nq, K), "<i4")
+    land_d = pkg.device_view(p_d, (nq, K), "<f4")
     def step(i, events=None):
         q = batches[i % 2]
         router.scatter(q.data_ptr(), nq, stream=stream)
@@ -336,30 +368,40 @@ def partitioned_block(pkg, args, dist, rank, world, dev, local_rank, peak):
     torch.cuda.synchronize()
     sent, received = router.counts(stream=stream)
     rec = recall_at_k(land_i[:nrec], gt)
+    routed_identical = float((land_i == whole_ids).all(1).float().mean())
     phase = dict(route_scatter_ms=round(ev[0].elapsed_time(ev[1]), 3), search_ms=round(ev[1].elapsed_time(ev[2]), 3),
                  search_kernel_ms=round(st["kernel_ms"], 3), allgather_ms=round(ev[2].elapsed_time(ev[3]), 3))
-    tot = max(1, st["rows_hot"] + st["rows_local"] + st["rows_remote"])
+    tot = max(1, st["rows_hot"] + st["rows_local"] + st["rows_remote"] + st["rows_halo"])
     remote_bytes = st["rows_remote"] * (4 * wl["dim"]) + (st["rows_remote"] / tot) * st["lists_l0"] * 8 * wl["m"]
     t = torch.tensor([total_ms, phase["search_kernel_ms"], remote_bytes / max(1e-9, st["kernel_ms"] * 1e-3) / 1e9,
                       st["algorithmic_bytes"] / max(1e-9, st["kernel_ms"] * 1e-3) / 1e9], device=dev, dtype=torch.float64)
     tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    frac = torch.tensor([st["rows_hot"], st["rows_local"], st["rows_remote"], st["processed"]], device=dev, dtype=torch.float64)
+    frac = torch.tensor([st["rows_hot"], st["rows_local"], st["rows_remote"], st["processed"], st["rows_halo"], halo_rows],
+                        device=dev, dtype=torch.float64)
     dist.all_reduce(frac)
+    ident = torch.tensor([part_identical, routed_identical], device=dev, dtype=torch.float64)
+    dist.all_reduce(ident, op=dist.ReduceOp.MIN)
     router.close(); part.close()
     torch.cuda.empty_cache()
     if rank != 0:
         return None
     total_ms = float(tmax[0])
     qps = world * nq * steps / (total_ms * 1e-3)
-    rows = float(frac[0] + frac[1] + frac[2])
-    return dict(workload=wl["label"], ef=ef, k=K, recall_at_10=round(rec, 4), value=round(qps, 1), unit="queries/s",
+    rows = float(frac[0] + frac[1] + frac[2] + frac[4])
+    return dict(workload=wl["label"], ef=ef, k=K, recall_at_10=round(rec, 4), recall_whole_index=whole["recall"],
+                identical_to_whole_index=dict(partition_unrouted=round(float(ident[0]), 6), routed=round(float(ident[1]), 6),
+                                              note="fraction of the step's queries whose id list equals the whole-index answer, min over ranks"),
+                processed_all_ranks=int(frac[3]), value=round(qps, 1), unit="queries/s",
                 steps=steps, ms_per_step=round(total_ms / steps, 3), queries_per_step_per_gpu=nq,
-                design="graph partitioned by k-means cluster over the GPUs' HBM + replicated hot set; remote hops = NVLink peer loads; "
+                design="graph partitioned by k-means cluster over the GPUs' HBM + replicated hot set + per-GPU halo (local copies of the "
+                       "peer-owned rows the GPU's routed queries read most); remote hops = NVLink peer loads; "
                        "queries routed on the GPU and delivered into peer-mapped inboxes, results written to the home GPU's landing "
                        "buffer by the search kernel; NCCL all-gather of the top-k lists",
                 whole_index_qps_per_gpu=whole["whole_index_qps_per_gpu"],
                 efficiency_vs_whole_index_replicas=round(qps / (world * whole["whole_index_qps_per_gpu"]), 4),
                 rows_hot=round(float(frac[0]) / rows, 4), rows_local=round(float(frac[1]) / rows, 4), rows_remote=round(float(frac[2]) / rows, 4),
+                rows_halo=round(float(frac[4]) / rows, 4), halo_ratio_pct=args.halo_ratio,
+                halo_rows_per_gpu=int(float(frac[5]) / world),
                 nvlink_in_gbs_max=round(float(tmax[2]), 1), nvlink_peak_gbs=770.0, nvlink_frac=round(float(tmax[2]) / 770.0, 4),
                 hbm_alg_gbs_per_gpu=round(float(t[3]), 1), hbm_frac=round(float(t[3]) / peak, 4),
                 cache_ratio_pct=args.cache_ratio, route_slack=args.route_slack, step_ms_rank0=phase,
@@ -391,6 +433,9 @@ def main():
     ap.add_argument("--part-steps", type=int, default=5)
     ap.add_argument("--part-recall-queries", type=int, default=5_000)
     ap.add_argument("--cache-ratio", type=int, default=8, help="partitioned: replicated hot set in %% of the nodes (--cache-ratio of the reference)")
+    ap.add_argument("--halo-ratio", type=int, default=8,
+                    help="partitioned: every GPU also caches this %% of the nodes from its peers' shares — the rows its own routed "
+                         "queries read most (shn_index_partition_build_halo); 0 = off")
     ap.add_argument("--route-slack", type=float, default=0.25, help="a GPU takes at most (1 + slack) / N of a batch (query_router.hh:106-151)")
     ap.add_argument("--partitioned", default="auto", choices=["auto", "off", "only"],
                     help="auto: measured when N > 1; off: replica headline only; only: skip the headline (development)")

@@ -194,7 +194,7 @@ void fill_stats(const shn_index* ix, const unsigned long long* t, uint64_t nq, s
   s->reference_layout_bytes = ref_node_bytes(ix->dim) * (t[kDistcomps] - nq) + ref_list0_bytes(ix->m) * t[kListsL0] +
                               ref_listu_bytes(ix->m) * t[kListsUpper];
   s->overflow_queries = t[kOverflowQueries];
-  s->rows_hot = t[kRowsHot]; s->rows_local = t[kRowsLocal]; s->rows_remote = t[kRowsRemote];
+  s->rows_hot = t[kRowsHot]; s->rows_local = t[kRowsLocal]; s->rows_remote = t[kRowsRemote]; s->rows_halo = t[kRowsHalo];
   s->processed = nq;
 }
 
@@ -435,7 +435,8 @@ void shn_index_free(shn_index* ix) {
   cudaFree(ix->d_level);
   for (int i = 0; i < 8; ++i) { vmm_free(ix->peer_vec_blk[i]); vmm_free(ix->peer_l0_blk[i]); }
   vmm_free(ix->own_vec_blk); vmm_free(ix->own_l0_blk);
-  cudaFree(ix->d_part_vec); cudaFree(ix->d_part_l0); cudaFree(ix->d_visits);
+  cudaFree(ix->d_visits);
+  cudaFree(ix->d_halo_dir); cudaFree(ix->d_halo_vec); cudaFree(ix->d_halo_l0);
   cudaFree(ix->ws.counter); cudaFree(ix->ws.totals);
   ix->ovf.release(); ix->q_stage.release(); ix->dist_stage.release(); ix->id_stage.release();
   for (auto& e : ix->ev) if (e) cudaEventDestroy(e);
@@ -449,6 +450,14 @@ uint32_t shn_index_dim(const shn_index* ix) { return ix ? ix->dim : 0; }
 uint32_t shn_index_m(const shn_index* ix) { return ix ? ix->m : 0; }
 uint32_t shn_index_max_level(const shn_index* ix) { return ix ? ix->max_level : 0; }
 uint64_t shn_index_hbm_bytes(const shn_index* ix) { return ix ? ix->hbm_bytes : 0; }
+int shn_index_partition_info(const shn_index* ix, uint32_t* hot, uint32_t* own, uint32_t* entry_row) {
+  if (!ix) return fail(SHN_ERR_ARG, "null index");
+  if (ix->world < 2) return fail(SHN_ERR_STATE, "the handle is not a partition");
+  if (hot) *hot = ix->hot;
+  if (own) *own = ix->own;
+  if (entry_row) *entry_row = ix->ep_row;
+  return SHN_OK;
+}
 uint64_t shn_index_dump_bytes(const shn_index* ix) { return ix ? ix->dump_bytes : 0; }
 
 int shn_set_option(shn_index* ix, const char* key, int64_t value) {
@@ -526,7 +535,7 @@ int shn_search(shn_index* ix, const float* queries, uint64_t nq, uint32_t k, uin
 
 int shn_index_count_visits(shn_index* ix, int enable) {
   if (!ix) return fail(SHN_ERR_ARG, "null index handle");
-  if (ix->world > 1) return fail(SHN_ERR_STATE, "visit counting belongs to the full index, before it is partitioned");
+  if (ix->world > 1 && ix->d_halo_dir && enable) return fail(SHN_ERR_STATE, "this partition already has its halo");
   CU(cudaSetDevice(ix->gpu));
   CU(cudaStreamSynchronize(ix->stream));
   if (!enable) { cudaFree(ix->d_visits); ix->d_visits = nullptr; return SHN_OK; }
@@ -549,6 +558,60 @@ int shn_index_visit_counts(shn_index* ix, uint32_t* d_counts, int write_back) {
   return SHN_OK;
 }
 
+int shn_index_partition_build_halo(shn_index* ix, uint32_t ratio_pct, uint64_t* halo_rows) {
+  if (!ix) return fail(SHN_ERR_ARG, "null index");
+  if (ix->world < 2) return fail(SHN_ERR_STATE, "the handle is not a partition");
+  if (ix->attached != ix->world) return fail(SHN_ERR_STATE, "partitioned handle: %u of %u partitions attached", ix->attached, ix->world);
+  if (ix->d_halo_dir) return fail(SHN_ERR_STATE, "this partition already has its halo");
+  if (!ix->d_visits) return fail(SHN_ERR_STATE, "visit counting is off: the halo is chosen from the counts of a warm-up pass");
+  if (ratio_pct > 100) return fail(SHN_ERR_ARG, "the halo budget is a percentage of the nodes");
+  CU(cudaSetDevice(ix->gpu));
+  CU(cudaStreamSynchronize(ix->stream));
+  const uint32_t n = ix->n, H = ix->hot;
+  std::vector<uint32_t> visits(n);
+  CU(cudaMemcpy(visits.data(), ix->d_visits, static_cast<size_t>(n) * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  cudaFree(ix->d_visits); ix->d_visits = nullptr;
+  // candidates: rows another GPU owns that this GPU's warm-up queries read at least once
+  uint32_t own_lo = 0, own_hi = 0;  // clustered: this GPU owns [own_lo, own_hi)
+  if (ix->clustered) { own_lo = ix->part_begin[ix->rank]; own_hi = ix->part_begin[ix->rank + 1]; }
+  auto mine = [&](uint32_t r) { return ix->clustered ? (r >= own_lo && r < own_hi) : ((r - H) % ix->world == ix->rank); };
+  std::vector<uint32_t> cand;
+  for (uint32_t r = H; r < n; ++r) if (visits[r] > 0 && !mine(r)) cand.push_back(r);
+  const uint64_t want = std::min<uint64_t>(static_cast<uint64_t>(n) * ratio_pct / 100, cand.size());
+  auto hotter = [&](uint32_t a, uint32_t b) { return visits[a] != visits[b] ? visits[a] > visits[b] : a < b; };
+  if (want < cand.size()) std::nth_element(cand.begin(), cand.begin() + want, cand.end(), hotter);
+  cand.resize(want);
+  std::sort(cand.begin(), cand.end());  // slots in row order: slot = prefix + popc(bits below)
+  if (halo_rows) *halo_rows = want;
+  if (want == 0) return SHN_OK;
+  const size_t words = (static_cast<size_t>(n - H) + 31) / 32;
+  std::vector<uint2> dir(words, make_uint2(0u, 0u));
+  for (uint32_t r : cand) dir[(r - H) >> 5].x |= 1u << ((r - H) & 31u);
+  uint32_t run = 0;
+  for (size_t w = 0; w < words; ++w) { dir[w].y = run; run += static_cast<uint32_t>(__builtin_popcount(dir[w].x)); }
+  const size_t row_bytes = static_cast<size_t>(ix->row_f4) * 16, m0 = 2ull * ix->m;
+  uint32_t* d_rows = nullptr;
+  uint2* d_dir = nullptr;
+  float4* d_vec = nullptr;
+  uint32_t* d_l0 = nullptr;
+  cudaError_t e = cudaMalloc(&d_rows, want * sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaMalloc(&d_dir, words * sizeof(uint2));
+  if (e == cudaSuccess) e = cudaMalloc(&d_vec, want * row_bytes);
+  if (e == cudaSuccess) e = cudaMalloc(&d_l0, want * m0 * sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_rows, cand.data(), want * sizeof(uint32_t), cudaMemcpyHostToDevice, ix->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_dir, dir.data(), words * sizeof(uint2), cudaMemcpyHostToDevice, ix->stream);
+  if (e == cudaSuccess) e = halo_gather(ix->view(), d_rows, static_cast<uint32_t>(want), d_vec, d_l0, ix->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ix->stream);
+  cudaFree(d_rows);
+  if (e != cudaSuccess) {
+    cudaFree(d_dir); cudaFree(d_vec); cudaFree(d_l0);
+    return fail(SHN_ERR_CUDA, "building the halo (%llu rows): %s", static_cast<unsigned long long>(want), cudaGetErrorString(e));
+  }
+  ix->d_halo_dir = d_dir; ix->d_halo_vec = d_vec; ix->d_halo_l0 = d_l0; ix->halo = static_cast<uint32_t>(want);
+  ix->hbm_bytes += want * (row_bytes + m0 * 4) + words * sizeof(uint2);
+  return SHN_OK;
+}
+
 int shn_index_partition(shn_index** out, const shn_index* full, int rank, int world, uint32_t cache_ratio_pct,
                         const uint8_t* d_owner) {
   if (!out || !full) return fail(SHN_ERR_ARG, "null argument");
@@ -568,6 +631,7 @@ int shn_index_partition(shn_index** out, const shn_index* full, int rank, int wo
   std::vector<uint8_t> is_hot(n, 0);
   uint64_t hot = 0;
   for (uint32_t r = 0; r < n; ++r) if (level[r] > 0) { is_hot[r] = 1; ++hot; }
+  if (!is_hot[full->ep_row]) { is_hot[full->ep_row] = 1; ++hot; }  // a graph with one level: the entry point is read by every query
   const uint64_t budget = std::min<uint64_t>(n, std::max<uint64_t>(hot, static_cast<uint64_t>(n) * cache_ratio_pct / 100));
   if (hot < budget && !visits.empty()) {
     std::vector<uint32_t> cand;
@@ -635,10 +699,6 @@ int shn_index_partition(shn_index** out, const shn_index* full, int rank, int wo
     ix->d_own_vec = static_cast<float4*>(ix->own_vec_blk.ptr);
     ix->d_own_l0 = static_cast<uint32_t*>(ix->own_l0_blk.ptr);
   }
-  CUB(cudaMalloc(&ix->d_part_vec, 8 * sizeof(void*)));
-  CUB(cudaMalloc(&ix->d_part_l0, 8 * sizeof(void*)));
-  CUB(cudaMemset(ix->d_part_vec, 0, 8 * sizeof(void*)));
-  CUB(cudaMemset(ix->d_part_l0, 0, 8 * sizeof(void*)));
   ix->hbm_bytes = H * (row_bytes + m0 * 4 + 4) + own * (row_bytes + m0 * 4) + n * 4ull + std::max<size_t>(ix->n_up, 1) * ix->m * 4;
   PartitionJob job;
   job.n = n; job.hot = H; job.own = own; job.rank = d_owner ? 0 : rank; job.world = d_owner ? 1 : world;
@@ -651,10 +711,8 @@ int shn_index_partition(shn_index** out, const shn_index* full, int rank, int wo
   if (e == cudaSuccess) e = cudaStreamSynchronize(ix->stream);
   cudaFree(d_new_of_old); cudaFree(d_old_of_new);
   if (e != cudaSuccess) return bail(fail(SHN_ERR_CUDA, "partition_arrays: %s", cudaGetErrorString(e)));
-  const void* vp = ix->d_own_vec;
-  const void* lp = ix->d_own_l0;
-  CUB(cudaMemcpy(ix->d_part_vec + rank, &vp, sizeof(void*), cudaMemcpyHostToDevice));
-  CUB(cudaMemcpy(ix->d_part_l0 + rank, &lp, sizeof(void*), cudaMemcpyHostToDevice));
+  ix->part_vec[rank] = ix->d_own_vec;
+  ix->part_l0[rank] = ix->d_own_l0;
 #undef CUB
   *out = ix;
   return SHN_OK;
@@ -813,8 +871,8 @@ int shn_index_partition_attach(shn_index* ix, int peer, const int* fds, const ui
       return fail(SHN_ERR_CUDA, "mapping the share of rank %d: %s failed", peer, why);
     vp = ix->peer_vec_blk[peer].ptr; lp = ix->peer_l0_blk[peer].ptr;
   }
-  CU(cudaMemcpy(ix->d_part_vec + peer, &vp, sizeof(void*), cudaMemcpyHostToDevice));
-  CU(cudaMemcpy(ix->d_part_l0 + peer, &lp, sizeof(void*), cudaMemcpyHostToDevice));
+  ix->part_vec[peer] = static_cast<const float4*>(vp);
+  ix->part_l0[peer] = static_cast<const uint32_t*>(lp);
   ++ix->attached;
   return SHN_OK;
 }
@@ -850,8 +908,8 @@ int shn_debug_select_neighbors(shn_index* ix, const uint32_t* cand_rows, const f
 double shn_debug_partition_gather_gbs(shn_index* ix, int part) {
   if (!ix || ix->world < 2 || part < 0 || part >= static_cast<int>(ix->world)) return -1.0;
   cudaSetDevice(ix->gpu);
-  const float4* ptr = nullptr;
-  if (cudaMemcpy(&ptr, ix->d_part_vec + part, sizeof ptr, cudaMemcpyDeviceToHost) != cudaSuccess || !ptr) return -1.0;
+  const float4* ptr = ix->part_vec[part];
+  if (!ptr) return -1.0;
   const uint32_t cold = ix->n - ix->hot;
   const uint32_t rows = ix->clustered ? ix->part_begin[part + 1] - ix->part_begin[part]
                                       : (cold > static_cast<uint32_t>(part) ? (cold - part + ix->world - 1) / ix->world : 0);

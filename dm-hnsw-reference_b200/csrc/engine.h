@@ -12,7 +12,7 @@ namespace shn {
 
 // Indices into the device-side totals array (u64 each), summed over the queries of one launch.
 enum Total { kDistcomps = 0, kVisitedUpper, kVisitedL0, kListsL0, kListsUpper, kOverflowQueries, kFailedQueries,
-             kRowsHot, kRowsLocal, kRowsRemote, kProcessed, kNumTotals };
+             kRowsHot, kRowsLocal, kRowsRemote, kRowsHalo, kProcessed, kNumTotals };
 
 // Per-query counter record written when the caller asks for it (shn_search_device per_query_counters).
 constexpr int kPerQueryWords = 6;  // distcomps, visited_nodes, visited_nodes_l0, lists_l0, lists_upper, overflow
@@ -80,6 +80,8 @@ struct PartitionJob {
 };
 cudaError_t partition_arrays(const PartitionJob& job, cudaStream_t stream);
 cudaError_t gather_rows(const float4* src, const uint32_t* d_rows, uint32_t count, uint32_t row_f4, float4* dst, cudaStream_t s);
+// halo (graph.h): copy the rows d_rows[count] of the partitioned graph g (g.halo_dir must be null) into dst_vec / dst_l0
+cudaError_t halo_gather(const DeviceGraph& g, const uint32_t* d_rows, uint32_t count, float4* dst_vec, uint32_t* dst_l0, cudaStream_t s);
 cudaError_t probe_gather(const float4* src, uint32_t nrows, uint32_t row_f4, double* gbs, cudaStream_t stream);
 
 // ---- placement and routing (placement.cu)

@@ -89,9 +89,16 @@ struct DeviceGraph {
   uint32_t hot, world, rank;
   uint32_t clustered;       // 0: row r >= hot lives on GPU (r-hot) % world; 1: GPU p owns rows [part_begin[p], part_begin[p+1])
   uint32_t part_begin[9];   // clustered placement (placement.cu); entries beyond `world` are 0xFFFFFFFF
-  const float4* const* part_vec;
-  const uint32_t* const* part_l0;
+  const float4* part_vec[8];   // base of every GPU's share as this GPU addresses it (kernel parameter = constant bank)
+  const uint32_t* part_l0[8];
   uint32_t* visit_count;  // optional [n]: +1 per level-0 distance computation (warm-up pass that picks the hot set)
+  // Halo (shn_index_partition_build_halo): local copies of the peer-owned rows THIS GPU's queries read most — with query
+  // routing a GPU's queries stay near its own cluster, and what they read remotely are the same border rows again and
+  // again.  The directory holds one {bits, prefix} pair per 32 rows >= hot (bit i: row hot + 32 w + i is in the halo;
+  // prefix: halo rows before word w), n/4 bytes in all, so it stays in L2; a row's slot is prefix + popc(bits below).
+  const uint2* halo_dir;     // nullptr = no halo
+  const float4* halo_vec;    // [halo][row_f4]
+  const uint32_t* halo_l0;   // [halo][2m]
 };
 
 #ifdef __CUDACC__
@@ -111,20 +118,41 @@ __device__ __forceinline__ void locate_row(const DeviceGraph& g, uint32_t row, u
     idx = o / g.world;
   }
 }
+// Where a row lives, as this GPU sees it: loc < 8 = the share of GPU loc (own or peer-mapped), kLocHot = the replicated
+// hot set, kLocHalo = this GPU's halo; idx = the row's index there.
+constexpr uint32_t kLocHot = 8, kLocHalo = 9;
+__device__ __forceinline__ void resolve_row(const DeviceGraph& g, uint32_t row, uint32_t& loc, uint32_t& idx) {
+  if (row < g.hot) { loc = kLocHot; idx = row; return; }
+  locate_row(g, row, loc, idx);
+  if (loc != g.rank && g.halo_dir) {
+    const uint32_t o = row - g.hot;
+    const uint2 e = __ldg(g.halo_dir + (o >> 5));
+    const uint32_t bit = 1u << (o & 31u);
+    if (e.x & bit) { loc = kLocHalo; idx = e.y + __popc(e.x & (bit - 1u)); }
+  }
+}
+__device__ __forceinline__ const float4* vec_at(const DeviceGraph& g, uint32_t loc, uint32_t idx) {
+  const float4* base = loc == kLocHot ? g.vec : (loc == kLocHalo ? g.halo_vec : g.part_vec[loc]);
+  return base + static_cast<size_t>(idx) * g.row_f4;
+}
+__device__ __forceinline__ const uint32_t* l0_at(const DeviceGraph& g, uint32_t loc, uint32_t idx) {
+  const uint32_t* base = loc == kLocHot ? g.l0 : (loc == kLocHalo ? g.halo_l0 : g.part_l0[loc]);
+  return base + static_cast<size_t>(idx) * g.m0;
+}
 // PART = false: the handle holds every row (one GPU, or the builder): no placement test in the instruction stream
 template <bool PART>
 __device__ __forceinline__ const float4* vec_row(const DeviceGraph& g, uint32_t row) {
   if (!PART || row < g.hot) return g.vec + static_cast<size_t>(row) * g.row_f4;
-  uint32_t part, idx;
-  locate_row(g, row, part, idx);
-  return g.part_vec[part] + static_cast<size_t>(idx) * g.row_f4;
+  uint32_t loc, idx;
+  resolve_row(g, row, loc, idx);
+  return vec_at(g, loc, idx);
 }
 template <bool PART>
 __device__ __forceinline__ const uint32_t* l0_row(const DeviceGraph& g, uint32_t row) {
   if (!PART || row < g.hot) return g.l0 + static_cast<size_t>(row) * g.m0;
-  uint32_t part, idx;
-  locate_row(g, row, part, idx);
-  return g.part_l0[part] + static_cast<size_t>(idx) * g.m0;
+  uint32_t loc, idx;
+  resolve_row(g, row, loc, idx);
+  return l0_at(g, loc, idx);
 }
 #endif
 

@@ -225,4 +225,28 @@ int shn_group_search(shn_group* grp, const float* queries, uint64_t nq, uint32_t
   return SHN_OK;
 }
 
+int shn_group_warmup(shn_group* grp, const float* queries, uint64_t nq, uint32_t k, uint32_t ef, uint32_t halo_ratio_pct,
+                     uint64_t* halo_rows) {
+  if (!grp || (!queries && nq)) return fail(SHN_ERR_ARG, "null argument");
+  if (halo_rows) *halo_rows = 0;
+  if (halo_ratio_pct) {
+    for (int g = 0; g < grp->n; ++g) {
+      const int rc = shn_index_count_visits(grp->part[g], 1);
+      if (rc != SHN_OK) return rc;
+    }
+  }
+  std::vector<uint32_t> ids(nq * k);
+  int rc = shn_group_search(grp, queries, nq, k, ef, ids.data(), nullptr, nullptr, nullptr);
+  if (rc != SHN_OK) return rc;
+  if (halo_ratio_pct) {
+    for (int g = 0; g < grp->n; ++g) {
+      uint64_t rows = 0;
+      rc = shn_index_partition_build_halo(grp->part[g], halo_ratio_pct, &rows);
+      if (rc != SHN_OK) return rc;
+      if (halo_rows) *halo_rows += rows;
+    }
+  }
+  return SHN_OK;
+}
+
 }  // extern "C"

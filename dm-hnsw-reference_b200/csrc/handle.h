@@ -80,11 +80,15 @@ struct shn_index {
   uint32_t part_begin[9] = {0};
   float4* d_own_vec = nullptr;
   uint32_t* d_own_l0 = nullptr;
-  const float4** d_part_vec = nullptr;   // device table [world]
-  const uint32_t** d_part_l0 = nullptr;
+  const float4* part_vec[8] = {nullptr};   // the shares as this GPU addresses them (own, or peer-mapped); travel to the
+  const uint32_t* part_l0[8] = {nullptr};  // kernels inside DeviceGraph, i.e. in the constant bank
   shn::VmmBlock own_vec_blk, own_l0_blk;      // this GPU's share (exportable as POSIX fds)
   shn::VmmBlock peer_vec_blk[8], peer_l0_blk[8];  // shares of other processes mapped here
   uint32_t* d_visits = nullptr;          // [n] when visit counting is on
+  uint2* d_halo_dir = nullptr;           // halo (graph.h): directory, rows, lists; halo = number of rows
+  float4* d_halo_vec = nullptr;
+  uint32_t* d_halo_l0 = nullptr;
+  uint32_t halo = 0;
   bool built = false;
 
   shn::DeviceGraph view() const {
@@ -92,8 +96,10 @@ struct shn_index {
     g.vec = d_vec; g.l0 = d_l0; g.up_base = d_up_base; g.up = d_up; g.ext_id = d_ext_id;
     g.n = n; g.dim = dim; g.m = m; g.m0 = 2 * m; g.row_f4 = row_f4; g.ep_row = ep_row; g.ep_level = max_level_of_ep;
     g.hot = world > 1 ? hot : n; g.world = world; g.rank = rank;
-    g.part_vec = d_part_vec; g.part_l0 = d_part_l0; g.visit_count = d_visits;
+    for (int i = 0; i < 8; ++i) { g.part_vec[i] = part_vec[i]; g.part_l0[i] = part_l0[i]; }
+    g.visit_count = d_visits;
     g.clustered = clustered;
+    g.halo_dir = d_halo_dir; g.halo_vec = d_halo_vec; g.halo_l0 = d_halo_l0;
     for (int i = 0; i < 9; ++i) g.part_begin[i] = part_begin[i];
     return g;
   }

@@ -62,6 +62,20 @@ __global__ void probe_gather_kernel(const float4* __restrict__ src, uint32_t nro
   if (acc == 123.456f) out[0] = acc;
 }
 
+// halo slot i <- row rows[i] of the partitioned graph, wherever it lives (a peer's share over NVLink, normally); a warp per row
+__global__ void halo_gather_kernel(const DeviceGraph g, const uint32_t* __restrict__ rows, uint32_t count, float4* __restrict__ dst_vec,
+                                   uint32_t* __restrict__ dst_l0) {
+  const uint32_t warps = gridDim.x * (blockDim.x >> 5);
+  const int lane = threadIdx.x & 31;
+  for (uint32_t i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < count; i += warps) {
+    const uint32_t row = rows[i];
+    const float4* v = vec_row<true>(g, row);
+    const uint32_t* l = l0_row<true>(g, row);
+    for (uint32_t f = lane; f < g.row_f4; f += 32) dst_vec[static_cast<size_t>(i) * g.row_f4 + f] = v[f];
+    for (uint32_t f = lane; f < g.m0; f += 32) dst_l0[static_cast<size_t>(i) * g.m0 + f] = l[f];
+  }
+}
+
 inline int grid_for(uint64_t work, int threads) {
   return static_cast<int>(std::max<uint64_t>(1, std::min<uint64_t>((work + threads - 1) / threads, 148ull * 16)));
 }
@@ -90,6 +104,12 @@ cudaError_t partition_arrays(const PartitionJob& j, cudaStream_t s) {
 cudaError_t gather_rows(const float4* src, const uint32_t* d_rows, uint32_t count, uint32_t row_f4, float4* dst, cudaStream_t s) {
   if (count == 0) return cudaSuccess;
   gather_rows_kernel<<<grid_for(static_cast<uint64_t>(count) * 32, 256), 256, 0, s>>>(src, d_rows, 0, 1, count, row_f4, dst);
+  return cudaGetLastError();
+}
+
+cudaError_t halo_gather(const DeviceGraph& g, const uint32_t* d_rows, uint32_t count, float4* dst_vec, uint32_t* dst_l0, cudaStream_t s) {
+  if (count == 0) return cudaSuccess;
+  halo_gather_kernel<<<grid_for(static_cast<uint64_t>(count) * 32, 256), 256, 0, s>>>(g, d_rows, count, dst_vec, dst_l0);
   return cudaGetLastError();
 }
 

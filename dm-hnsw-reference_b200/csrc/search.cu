@@ -42,10 +42,11 @@ struct SearchParams {
   RoutedIo io;
 };
 
-// per warp: launch totals | query | row/distance staging (one list) | queue distances | queue ids | visited table
+// per warp: launch totals | resolved row addresses (partitioned handles only) | query | row/distance staging (one list) |
+// queue distances | queue ids | visited table
 constexpr uint32_t kTotalsBytes = (kNumTotals * 8 + 15) / 16 * 16;
-__host__ __device__ inline size_t warp_smem_bytes(uint32_t q_floats, uint32_t ef_cap, uint32_t list_cap, uint32_t vis_cap) {
-  return kTotalsBytes + 4ull * (q_floats + 2 * list_cap + 2 * ef_cap + vis_cap);
+__host__ __device__ inline size_t warp_smem_bytes(uint32_t q_floats, uint32_t ef_cap, uint32_t list_cap, uint32_t vis_cap, bool part) {
+  return kTotalsBytes + (part ? 8ull * list_cap + 16ull * ((list_cap + 15) / 16) : 0ull) + 4ull * (q_floats + 2 * list_cap + 2 * ef_cap + vis_cap);
 }
 
 template <bool IP, int NCHUNK, bool PART>
@@ -56,10 +57,12 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, SHN_MIN_BLOCKS) search_ke
   const DeviceGraph& g = p.g;
 
   const uint32_t q_floats = NCHUNK > 0 ? row_stride_f4(NCHUNK) * 4u : p.q_floats;
-  unsigned char* base = smem_raw + warp * warp_smem_bytes(q_floats, p.ef_cap, p.list_cap, p.vis_cap);
+  unsigned char* base = smem_raw + warp * warp_smem_bytes(q_floats, p.ef_cap, p.list_cap, p.vis_cap, PART);
   // the launch totals live in shared memory (11 x 64 bit per warp would otherwise sit in registers for the whole kernel)
   unsigned long long* s_tot = reinterpret_cast<unsigned long long*>(base);
-  float* s_q = reinterpret_cast<float*>(base + kTotalsBytes);
+  const float4** s_ptr = reinterpret_cast<const float4**>(base + kTotalsBytes);
+  uint8_t* s_ord = reinterpret_cast<uint8_t*>(base + kTotalsBytes + 8u * p.list_cap);
+  float* s_q = reinterpret_cast<float*>(base + kTotalsBytes + (PART ? 8u * p.list_cap + 16u * ((p.list_cap + 15u) / 16u) : 0u));
   uint32_t* s_rows = reinterpret_cast<uint32_t*>(s_q + q_floats);
   float* s_dist = reinterpret_cast<float*>(s_rows + p.list_cap);
   float* qd = s_dist + p.list_cap;
@@ -123,9 +126,10 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, SHN_MIN_BLOCKS) search_ke
     visited_test_and_set(vis, cur, lane == 0, lane);
 
     // search_level<without_lock>(ef, level 0) (hnsw.hh:407-476)
-    uint32_t c_hot = 0, c_local = 0;
+    uint32_t c_hot = 0, c_local = 0, c_halo = 0;
     const uint32_t l0_before = c_vl0;
-    beam_search<IP, NCHUNK, PART>(g, s_q, 0, p.ef, qd, qi, qsize, s_rows, s_dist, vis, c_unused, c_vl0, c_l0, c_hot, c_local, lane);
+    beam_search<IP, NCHUNK, PART>(g, s_q, 0, p.ef, qd, qi, qsize, s_rows, s_dist, vis, c_unused, c_vl0, c_l0, c_hot, c_local, c_halo,
+                                  s_ptr, s_ord, lane);
 
     // trim to k (:296-298); the reference reports ids in heap-array order, here ascending by distance
     {
@@ -161,7 +165,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, SHN_MIN_BLOCKS) search_ke
       s_tot[kFailedQueries] += vis.failed ? 1u : 0u;
       s_tot[kProcessed] += 1;
       if (PART && g.world > 1) {
-        s_tot[kRowsHot] += c_hot; s_tot[kRowsLocal] += c_local; s_tot[kRowsRemote] += (c_vl0 - l0_before) - c_hot - c_local;
+        s_tot[kRowsHot] += c_hot; s_tot[kRowsLocal] += c_local; s_tot[kRowsHalo] += c_halo;
+        s_tot[kRowsRemote] += (c_vl0 - l0_before) - c_hot - c_local - c_halo;
       }
     }
     __syncwarp();
@@ -220,15 +225,15 @@ cudaError_t search_plan(const DeviceGraph& g, const SearchConfig& cfg, uint32_t 
   const uint32_t ef_cap = (cfg.ef + 31u) & ~31u;
   const uint32_t list_cap = g.m0 <= 32 ? 32u : 64u;
   uint32_t vis_cap = cfg.vis_cap ? next_pow2(cfg.vis_cap) : pick_vis_cap(cfg.ef, g.m0);
-  size_t bytes = kWarpsPerBlock * warp_smem_bytes(q_floats, ef_cap, list_cap, vis_cap);
+  const bool part = g.world > 1 || g.visit_count != nullptr;
+  size_t bytes = kWarpsPerBlock * warp_smem_bytes(q_floats, ef_cap, list_cap, vis_cap, part);
   while (bytes > 200 * 1024 && vis_cap > 1024) {
     vis_cap >>= 1;
-    bytes = kWarpsPerBlock * warp_smem_bytes(q_floats, ef_cap, list_cap, vis_cap);
+    bytes = kWarpsPerBlock * warp_smem_bytes(q_floats, ef_cap, list_cap, vis_cap, part);
   }
   if (bytes > 227 * 1024) return cudaErrorInvalidValue;
   int blocks = 0;
   const int v = chunk_variant(g.dim);
-  const bool part = g.world > 1 || g.visit_count != nullptr;
   cudaError_t e = DISPATCH(occupancy_t, cfg.ip, part, v, bytes, &blocks);
   if (e != cudaSuccess) return e;
   if (blocks < 1) return cudaErrorInvalidConfiguration;

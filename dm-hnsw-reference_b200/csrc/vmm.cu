@@ -1,6 +1,7 @@
 #include "vmm.h"
 
 #include <cstdint>
+#include <cstdlib>
 
 namespace shn {
 namespace {
@@ -90,6 +91,14 @@ cudaError_t map_block(const Driver& d, VmmBlock& b, int device, const char** why
 }  // namespace
 
 cudaError_t vmm_alloc(VmmBlock& b, size_t bytes, int device, const char** why) {
+  if (const char* plain = getenv("SHN_SHARE_PLAIN"); plain && plain[0] == '1') {
+    // diagnostic only (tools/part_overhead.py): a cudaMalloc share, usable by handles of the same process, not exportable
+    b = VmmBlock{};
+    b.size = bytes; b.plain = true;
+    const cudaError_t e = cudaMalloc(&b.ptr, bytes);
+    if (e != cudaSuccess) { *why = "cudaMalloc"; b = VmmBlock{}; }
+    return e;
+  }
   const Driver& d = driver();
   if (!d.ok) { *why = "CUDA driver lacks the virtual memory management API"; return cudaErrorNotSupported; }
   cudaFree(nullptr);  // make sure the primary context exists
@@ -110,7 +119,7 @@ cudaError_t vmm_alloc(VmmBlock& b, size_t bytes, int device, const char** why) {
 
 cudaError_t vmm_export_fd(const VmmBlock& b, int* fd, const char** why) {
   const Driver& d = driver();
-  if (!d.ok || !b.ptr) { *why = "nothing to export"; return cudaErrorInvalidValue; }
+  if (!d.ok || !b.ptr || b.plain) { *why = "nothing to export"; return cudaErrorInvalidValue; }
   int out = -1;
   if (d.MemExportToShareableHandle(&out, b.handle, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0) != CUDA_SUCCESS) {
     *why = "cuMemExportToShareableHandle"; return cudaErrorUnknown;
@@ -138,6 +147,7 @@ cudaError_t vmm_import_fd(VmmBlock& b, int fd, size_t size, int device, const ch
 
 void vmm_free(VmmBlock& b) {
   const Driver& d = driver();
+  if (b.plain) { cudaFree(b.ptr); b = VmmBlock{}; return; }
   if (!d.ok || !b.ptr) { b = VmmBlock{}; return; }
   const CUdeviceptr va = reinterpret_cast<CUdeviceptr>(b.ptr);
   d.MemUnmap(va, b.size);

@@ -17,6 +17,7 @@ struct VmmBlock {
   size_t size = 0;          // padded to the allocation granularity
   unsigned long long handle = 0;  // CUmemGenericAllocationHandle
   bool imported = false;
+  bool plain = false;       // SHN_SHARE_PLAIN=1 diagnostic: cudaMalloc instead of cuMemCreate
 };
 
 // Allocate `bytes` of device memory on `device`, read/write mapped for that device, exportable as a POSIX fd.

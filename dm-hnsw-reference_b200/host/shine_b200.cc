@@ -353,7 +353,7 @@ int main(int argc, char** argv) {
 
   std::vector<shn_index*> handles(n_gpus, nullptr);  // one GPU: the index; several: the full indexes until the group holds its partitions
   shn_group* group = nullptr;
-  double placement_kmeans_ms = 0.0, placement_fetch_ms = 0.0;
+  double placement_kmeans_ms = 0.0, placement_fetch_ms = 0.0, warmup_routing_ms = 0.0;
   for (int g = 0; g < n_gpus; ++g) {
     shn_index* full = make_full(cfg.gpu + g, g == 0);
     if (cfg.use_cache && warmup.n) {
@@ -371,9 +371,18 @@ int main(int argc, char** argv) {
     // memory nodes -> HBM partitions (NVLink peer reads), compute-node cache -> replicated hot set; with --routing the
     // nodes are placed by k-means cluster and the queries run on the GPU of their nearest centroid (compute_node.cc:110-131,
     // query_router.hh:280-387)
-    SHN(shn_group_create(&group, handles.data(), n_gpus, cfg.use_cache ? cfg.cache_ratio : 0, cfg.routing ? 1 : 0, cfg.routing ? 1 : 0,
-                         0.25, std::max<uint64_t>(1, queries.n), cfg.k, 1234));
+    // the cache budget (--cache-ratio, % of the nodes per compute node): without routing all of it is the replicated hot set;
+    // with routing half of it, the other half is each GPU's own halo (the peer-owned rows its routed queries read most)
+    const uint32_t cache_pct = cfg.use_cache ? cfg.cache_ratio : 0;
+    const uint32_t halo_pct = (cfg.routing && warmup.n) ? cache_pct / 2 : 0;
+    SHN(shn_group_create(&group, handles.data(), n_gpus, cache_pct - halo_pct, cfg.routing ? 1 : 0, cfg.routing ? 1 : 0,
+                         0.25, std::max<uint64_t>(1, std::max(queries.n, warmup.n)), cfg.k, 1234));
     for (int g = 0; g < n_gpus; ++g) { shn_index_free(handles[g]); handles[g] = nullptr; }
+    if (halo_pct) {
+      const double w0 = now_ms();
+      SHN(shn_group_warmup(group, warmup.f.data(), warmup.n, cfg.k, cfg.ef_search, halo_pct, nullptr));
+      warmup_routing_ms = now_ms() - w0;
+    }
     for (int g = 0; g < n_gpus; ++g) hbm_bytes += shn_index_hbm_bytes(shn_group_partition(group, g));
     SHN(shn_group_timings(group, &placement_kmeans_ms, &placement_fetch_ms));
   }
@@ -404,7 +413,7 @@ int main(int argc, char** argv) {
       st.distcomps += p.distcomps; st.visited_nodes += p.visited_nodes; st.visited_nodes_l0 += p.visited_nodes_l0;
       st.visited_neighborlists += p.visited_neighborlists; st.reference_layout_bytes += p.reference_layout_bytes;
       st.algorithmic_bytes += p.algorithmic_bytes; st.processed += p.processed;
-      st.rows_hot += p.rows_hot; st.rows_local += p.rows_local; st.rows_remote += p.rows_remote;
+      st.rows_hot += p.rows_hot + p.rows_halo; st.rows_local += p.rows_local; st.rows_remote += p.rows_remote;
       st.kernel_ms = std::max(st.kernel_ms, p.kernel_ms); st.h2d_ms = std::max(st.h2d_ms, p.h2d_ms); st.d2h_ms = std::max(st.d2h_ms, p.d2h_ms);
     }
   }
@@ -454,7 +463,7 @@ int main(int argc, char** argv) {
   out["cache"]["misses_total"] = st.rows_remote;
   out["cache"]["hit_rate"] = rate(st.rows_hot + st.rows_local, st.rows_remote);
   for (int g = 0; g < n_gpus; ++g)
-    out["cache"]["local_hit_rates"]["c" + std::to_string(g)] = rate(per_gpu[g].rows_hot + per_gpu[g].rows_local, per_gpu[g].rows_remote);
+    out["cache"]["local_hit_rates"]["c" + std::to_string(g)] = rate(per_gpu[g].rows_hot + per_gpu[g].rows_halo + per_gpu[g].rows_local, per_gpu[g].rows_remote);
   out["cache"]["local_size"] = uint64_t{0};
   out["cache"]["cached_nodes"] = uint64_t{0};
   out["cache"]["cache_buckets_size"] = uint64_t{0};
@@ -495,7 +504,7 @@ int main(int argc, char** argv) {
   tj["placement_fetch"] = placement_fetch_ms;    // several GPUs: splitting the index into the GPUs' shares
   tj["placement_kmeans"] = placement_kmeans_ms;  // --routing: k-means over the upper-level nodes + balanced assignment
   tj["routing"] = routing_ms;                    // --routing: route + deliver the batch (slowest GPU)
-  if (cfg.use_cache) tj["warmup_routing"] = 0.0;
+  if (cfg.use_cache) tj["warmup_routing"] = warmup_routing_ms;  // --routing: the routed warm-up pass that fills the GPUs' halos
 
   std::cerr << std::endl << "statistics:" << std::endl;
   out.dump(std::cout, 0);

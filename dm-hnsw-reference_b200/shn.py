@@ -24,7 +24,7 @@ class Stats(C.Structure):
                                           "lists_l0", "lists_upper", "algorithmic_bytes", "reference_layout_bytes",
                                           "overflow_queries", "processed")] + \
                [("kernel_ms", C.c_double), ("h2d_ms", C.c_double), ("d2h_ms", C.c_double)] + \
-               [(n, C.c_uint64) for n in ("rows_hot", "rows_local", "rows_remote")]
+               [(n, C.c_uint64) for n in ("rows_hot", "rows_local", "rows_remote", "rows_halo")]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -79,6 +79,8 @@ def lib():
         L.shn_route_queries.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_int, C.c_void_p, C.c_uint64, C.c_double, C.c_void_p, C.c_int]
         L.shn_index_partition_export.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.shn_index_partition_attach.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.shn_index_partition_info.argtypes = [C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+        L.shn_index_partition_build_halo.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_uint64)]
         L.shn_router_create.argtypes = [C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p, C.c_double, C.c_uint64, C.c_uint32]
         L.shn_router_free.argtypes = [C.c_void_p]
         L.shn_router_free.restype = None
@@ -225,6 +227,18 @@ class Index:
     @property
     def dump_bytes(self):
         return lib().shn_index_dump_bytes(self._h)
+
+    def build_halo(self, ratio_pct):
+        """After count_visits(True) + warm-up searches on this partition: cache the most-read peer-owned rows locally."""
+        rows = C.c_uint64()
+        _check(lib().shn_index_partition_build_halo(self._h, ratio_pct, C.byref(rows)))
+        return int(rows.value)
+
+    def partition_info(self):
+        """(hot, own, entry_row) of a partition handle."""
+        h, o, e = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        _check(lib().shn_index_partition_info(self._h, C.byref(h), C.byref(o), C.byref(e)))
+        return int(h.value), int(o.value), int(e.value)
 
     def set_option(self, key, value):
         _check(lib().shn_set_option(self._h, key.encode(), int(value)))

@@ -54,6 +54,7 @@ typedef struct {
   uint64_t rows_hot;              /* replicated hot set in local HBM (the compute-node cache of src/cache/cache.hh) */
   uint64_t rows_local;            /* this GPU's own partition */
   uint64_t rows_remote;           /* a peer's partition, over NVLink (what the reference READs over RDMA) */
+  uint64_t rows_halo;             /* this GPU's halo: local copies of peer-owned rows (shn_index_partition_build_halo); also cache hits */
 } shn_stats;
 
 /* ---- index lifetime -------------------------------------------------------------------------------------- */
@@ -144,6 +145,17 @@ int shn_placement_fit(const shn_index* full, int world, uint32_t seed, double sl
  * queries of this batch, in query order (query_router.hh:356-368).  d_queries: device [nq][dim]; dest: host [nq]. */
 int shn_route_queries(const float* centroids, int world, uint32_t dim, shn_metric metric, const float* d_queries, uint64_t nq,
                       double slack, uint8_t* dest, int gpu_id);
+/* Halo: a second, per-GPU cache on top of the replicated hot set.  With query routing a GPU's queries stay near its own
+ * cluster and what they still read from peers are the same border rows over and over (the reference's compute-node cache
+ * fills with exactly those, src/cache/cache.hh:232-311 admission on miss).  Protocol: shn_index_count_visits(partition, 1),
+ * run warm-up queries the way they will be served (routed), then this call: the ratio_pct % of the nodes that this GPU read
+ * most often among the rows its peers own are copied over NVLink into local HBM together with their level-0 lists; later
+ * searches read them locally (stats.rows_halo).  Results are unchanged.  halo_rows (may be NULL) receives the row count. */
+int shn_index_partition_build_halo(shn_index*, uint32_t ratio_pct, uint64_t* halo_rows);
+/* How the handle was cut: size of the replicated hot set, rows of this GPU's own share, the entry point in the partition's
+ * numbering.  Every rank of one partitioned index must report the same hot and entry_row (the ranks address each other's
+ * shares with their own numbering); any output may be NULL. */
+int shn_index_partition_info(const shn_index*, uint32_t* hot, uint32_t* own, uint32_t* entry_row);
 /* This GPU's share as two POSIX file descriptors (vectors, level-0 lists; CUDA virtual-memory-management export — the
  * caller passes them to the other processes over a Unix socket and closes them), their mapped sizes, and the raw device
  * pointers (for peers inside the same process).  Any of the three outputs may be NULL. */
@@ -204,6 +216,12 @@ int shn_group_timings(const shn_group*, double* placement_kmeans_ms, double* pla
  * slowest GPU's route + scatter time. */
 int shn_group_search(shn_group*, const float* queries, uint64_t nq, uint32_t k, uint32_t ef, uint32_t* out_ids,
                      float* out_dists, shn_stats* per_gpu, double* routing_ms);
+/* The warm-up pass of compute_node.cc:116-131 through the group (results discarded), served the way the queries will be
+ * (routed or round-robin).  halo_ratio_pct > 0: the pass counts what every GPU reads from its peers and each GPU then
+ * caches the halo_ratio_pct % most-read of those rows locally (shn_index_partition_build_halo); halo_rows (may be NULL)
+ * receives the total over the GPUs.  Once per group. */
+int shn_group_warmup(shn_group*, const float* queries, uint64_t nq, uint32_t k, uint32_t ef, uint32_t halo_ratio_pct,
+                     uint64_t* halo_rows);
 
 /* ---- search ------------------------------------------------------------------------------------------------ */
 

@@ -39,7 +39,7 @@ def test_library_is_sm100a_sass(pkg):
 
 
 def test_stats_struct_layout(pkg):
-    assert C.sizeof(pkg.shn.Stats) == 10 * 8 + 3 * 8 + 3 * 8
+    assert C.sizeof(pkg.shn.Stats) == 10 * 8 + 3 * 8 + 4 * 8
 
 
 def test_argument_errors_need_no_gpu(pkg):

@@ -113,6 +113,63 @@ def test_routed_step_matches_unrouted_search(pkg, world, ip, slack, skew):
             p.close()
 
 
+@pytest.mark.parametrize("world,halo_pct", [(2, 10), (4, 5), (4, 100)])
+def test_halo_keeps_the_answers_and_cuts_the_remote_reads(pkg, world, halo_pct):
+    """shn_index_partition_build_halo: after a routed warm-up pass with visit counting every (emulated) rank caches the
+    peer-owned rows it read most; the routed answers stay bit-identical to the unrouted search of the full index, the
+    halo rows show up as rows_halo, and the remote share drops (100 %: every row read in the warm-up pass is cached, so
+    repeating the same batch reads nothing remotely)."""
+    import torch
+    n, dim, nq = 30000, 32, 3000
+    base, queries = datagen.base_and_queries(n, world * nq, dim)
+    with pkg.Index.build(base, 16, 100) as full:
+        ref_ids, ref_d, _ = full.search(queries, 10, 64)
+        owner = torch.empty(n, dtype=torch.uint8, device="cuda")
+        cent, _ = full.placement_fit(world, owner.data_ptr(), slack=0.05)
+        parts, routers = make_group(pkg, full, world, owner.data_ptr(), cent, nq, 0.25)
+    try:
+        q_dev = [torch.from_numpy(queries[r * nq:(r + 1) * nq]).cuda() for r in range(world)]
+
+        def routed_step():
+            for r, rt in enumerate(routers):
+                rt.scatter(q_dev[r].data_ptr(), nq)
+            torch.cuda.synchronize()
+            stats = [rt.search(10, 64) for rt in routers]
+            torch.cuda.synchronize()
+            return stats
+
+        for p in parts:
+            p.count_visits(True)
+        before = routed_step()
+        halo_rows = [p.build_halo(halo_pct) for p in parts]
+        assert all(0 < h <= n * halo_pct // 100 for h in halo_rows)
+        with pytest.raises(pkg.ShnError):
+            parts[0].build_halo(halo_pct)          # once per partition
+        after = routed_step()
+        for r, rt in enumerate(routers):
+            p_ids, p_d = rt.results()
+            got_i = pkg.device_view(p_ids, (nq, 10), "<i4").cpu().numpy().view(np.uint32)
+            got_d = pkg.device_view(p_d, (nq, 10), "<f4").cpu().numpy()
+            sl = slice(r * nq, (r + 1) * nq)
+            assert (got_i == ref_ids[sl]).all() and (got_d.view(np.uint32) == ref_d[sl].view(np.uint32)).all()
+        for b, a in zip(before, after):
+            assert b["rows_halo"] == 0 and a["rows_halo"] > 0
+            assert a["rows_hot"] == b["rows_hot"] and a["rows_local"] == b["rows_local"]
+            assert a["rows_halo"] + a["rows_remote"] == b["rows_remote"]
+            if halo_pct == 100:
+                assert a["rows_remote"] == 0
+        rem_b = sum(s["rows_remote"] for s in before); rem_a = sum(s["rows_remote"] for s in after)
+        print(f"world {world}, halo {halo_pct}%: remote level-0 reads {rem_b} -> {rem_a}; halo rows {halo_rows}")
+        # the unrouted search of a partition also goes through the halo
+        ids0, d0, st0 = parts[0].search(queries[:500], 10, 64)
+        assert (ids0 == ref_ids[:500]).all() and st0["rows_halo"] > 0
+    finally:
+        for rt in routers:
+            rt.close()
+        for p in parts:
+            p.close()
+
+
 def test_router_on_a_single_gpu_index_and_errors(pkg):
     import torch
     base, queries = datagen.base_and_queries(5000, 700, 24)

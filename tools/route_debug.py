@@ -31,11 +31,12 @@ allcs = [torch.zeros_like(cs) for _ in range(world)]; dist.all_gather(allcs, cs)
 print(f"[{rank}] probe result checksum per rank {[int(x) for x in allcs]} (equal = identical graphs)", flush=True)
 if use_visits:
     ix.count_visits(True)
+    torch.cuda.synchronize()
     warm = bench.synth_rows(100000, dim, 7007 + rank, dev)
     tmp = torch.empty((100000, K), dtype=torch.int32, device=dev)
     ix.search_device(warm.data_ptr(), 100000, K, ef, tmp.data_ptr())
     counts = torch.empty(ix.n, dtype=torch.int32, device=dev)
-    ix.visit_counts(counts.data_ptr()); dist.all_reduce(counts); ix.visit_counts(counts.data_ptr(), write_back=True)
+    ix.visit_counts(counts.data_ptr()); dist.all_reduce(counts); torch.cuda.synchronize(); ix.visit_counts(counts.data_ptr(), write_back=True)
 owner = torch.empty(n, dtype=torch.uint8, device=dev)
 cent, sizes = ix.placement_fit(world, owner.data_ptr(), seed=1234, slack=0.05)
 oh = torch.zeros(1, dtype=torch.int64, device=dev) + int(owner.long().mul(torch.arange(n, device=dev) % 1000003).sum())
