@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(kBuildWarps * 32, 4) insert_search_kernel(cons
       uint32_t qsize = 1;
       visited_test_and_set(vis, cur, lane == 0, lane);
       uint32_t c_hot = 0, c_local = 0;
-      beam_search<IP, NCHUNK>(g, s_q, lv, p.efc, qd, qi, qsize, s_rows, s_dist, vis, c_dist, c_vis, c_lists, c_hot, c_local, c_hot, nullptr, nullptr, lane);
+      beam_search<IP, NCHUNK>(g, s_q, lv, p.efc, qd, qi, qsize, s_rows, s_dist, vis, c_dist, c_vis, c_lists, c_hot, c_local, c_hot, nullptr, lane);
 
       const uint32_t ns = select_neighbors<IP, NCHUNK>(g, qi, qd, qsize, m, s_c, sel_rows, sel_dist, s_tmp, t_dist, lane);
 

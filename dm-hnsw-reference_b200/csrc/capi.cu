@@ -431,12 +431,35 @@ void shn_index_free(shn_index* ix) {
   if (!ix) return;
   cudaSetDevice(ix->gpu);
   if (ix->stream) cudaStreamSynchronize(ix->stream);
-  cudaFree(ix->d_vec); cudaFree(ix->d_l0); cudaFree(ix->d_up_base); cudaFree(ix->d_up); cudaFree(ix->d_ext_id);
+  if (ix->world > 1) {
+    // a partition: d_vec / d_l0 are address ranges; unmap every piece, drop the allocations, give the ranges back
+    const size_t row_bytes = static_cast<size_t>(ix->row_f4) * 16, list_bytes = 2ull * ix->m * sizeof(uint32_t);
+    if (ix->hot_vec_blk.handle) { vmm_unplace(ix->vec_space, 0, ix->hot_vec_blk.size); vmm_unplace(ix->l0_space, 0, ix->hot_l0_blk.size); }
+    if (ix->own_vec_blk.handle) {
+      vmm_unplace(ix->vec_space, ix->part_begin[ix->rank] * row_bytes, ix->own_vec_blk.size);
+      vmm_unplace(ix->l0_space, ix->part_begin[ix->rank] * list_bytes, ix->own_l0_blk.size);
+    }
+    for (uint32_t p = 0; p < 8; ++p) {
+      if (ix->peer_placed[p]) {
+        vmm_unplace(ix->vec_space, ix->part_begin[p] * row_bytes, ix->peer_vec_bytes[p]);
+        vmm_unplace(ix->l0_space, ix->part_begin[p] * list_bytes, ix->peer_l0_bytes[p]);
+      }
+      vmm_drop(ix->peer_vec_blk[p]); vmm_drop(ix->peer_l0_blk[p]);
+    }
+    if (ix->halo_vec_blk.handle) {
+      vmm_unplace(ix->vec_space, ix->n_ids * row_bytes, ix->halo_vec_blk.size);
+      vmm_unplace(ix->l0_space, ix->n_ids * list_bytes, ix->halo_l0_blk.size);
+    }
+    vmm_drop(ix->hot_vec_blk); vmm_drop(ix->hot_l0_blk); vmm_drop(ix->own_vec_blk); vmm_drop(ix->own_l0_blk);
+    vmm_drop(ix->halo_vec_blk); vmm_drop(ix->halo_l0_blk);
+    vmm_release(ix->vec_space); vmm_release(ix->l0_space);
+  } else {
+    cudaFree(ix->d_vec); cudaFree(ix->d_l0);
+  }
+  cudaFree(ix->d_up_base); cudaFree(ix->d_up); cudaFree(ix->d_ext_id);
   cudaFree(ix->d_level);
-  for (int i = 0; i < 8; ++i) { vmm_free(ix->peer_vec_blk[i]); vmm_free(ix->peer_l0_blk[i]); }
-  vmm_free(ix->own_vec_blk); vmm_free(ix->own_l0_blk);
   cudaFree(ix->d_visits);
-  cudaFree(ix->d_halo_dir); cudaFree(ix->d_halo_vec); cudaFree(ix->d_halo_l0);
+  cudaFree(ix->d_halo_dir);
   cudaFree(ix->ws.counter); cudaFree(ix->ws.totals);
   ix->ovf.release(); ix->q_stage.release(); ix->dist_stage.release(); ix->id_stage.release();
   for (auto& e : ix->ev) if (e) cudaEventDestroy(e);
@@ -539,8 +562,9 @@ int shn_index_count_visits(shn_index* ix, int enable) {
   CU(cudaSetDevice(ix->gpu));
   CU(cudaStreamSynchronize(ix->stream));
   if (!enable) { cudaFree(ix->d_visits); ix->d_visits = nullptr; return SHN_OK; }
-  if (!ix->d_visits) CU(cudaMalloc(&ix->d_visits, static_cast<size_t>(ix->n) * sizeof(uint32_t)));
-  CU(cudaMemsetAsync(ix->d_visits, 0, static_cast<size_t>(ix->n) * sizeof(uint32_t), ix->stream));
+  const size_t ids = ix->world > 1 ? ix->n_ids : ix->n;
+  if (!ix->d_visits) CU(cudaMalloc(&ix->d_visits, ids * sizeof(uint32_t)));
+  CU(cudaMemsetAsync(ix->d_visits, 0, ids * sizeof(uint32_t), ix->stream));
   CU(cudaStreamSynchronize(ix->stream));
   return SHN_OK;
 }
@@ -548,6 +572,7 @@ int shn_index_count_visits(shn_index* ix, int enable) {
 int shn_index_visit_counts(shn_index* ix, uint32_t* d_counts, int write_back) {
   if (!ix || !d_counts) return fail(SHN_ERR_ARG, "null argument");
   if (!ix->d_visits) return fail(SHN_ERR_STATE, "visit counting is off");
+  if (ix->world > 1) return fail(SHN_ERR_STATE, "the counters of a partition are consumed by shn_index_partition_build_halo");
   CU(cudaSetDevice(ix->gpu));
   CU(cudaStreamSynchronize(ix->stream));
   // on the handle's stream and complete on return (a device-to-device cudaMemcpy on the legacy stream is neither ordered
@@ -567,48 +592,60 @@ int shn_index_partition_build_halo(shn_index* ix, uint32_t ratio_pct, uint64_t* 
   if (ratio_pct > 100) return fail(SHN_ERR_ARG, "the halo budget is a percentage of the nodes");
   CU(cudaSetDevice(ix->gpu));
   CU(cudaStreamSynchronize(ix->stream));
-  const uint32_t n = ix->n, H = ix->hot;
-  std::vector<uint32_t> visits(n);
-  CU(cudaMemcpy(visits.data(), ix->d_visits, static_cast<size_t>(n) * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  const uint32_t ids = ix->n_ids;
+  std::vector<uint32_t> visits(ids);
+  CU(cudaMemcpy(visits.data(), ix->d_visits, static_cast<size_t>(ids) * sizeof(uint32_t), cudaMemcpyDeviceToHost));
   cudaFree(ix->d_visits); ix->d_visits = nullptr;
-  // candidates: rows another GPU owns that this GPU's warm-up queries read at least once
-  uint32_t own_lo = 0, own_hi = 0;  // clustered: this GPU owns [own_lo, own_hi)
-  if (ix->clustered) { own_lo = ix->part_begin[ix->rank]; own_hi = ix->part_begin[ix->rank + 1]; }
-  auto mine = [&](uint32_t r) { return ix->clustered ? (r >= own_lo && r < own_hi) : ((r - H) % ix->world == ix->rank); };
+  // candidates: rows of the peers' shares that this GPU's warm-up queries read at least once
   std::vector<uint32_t> cand;
-  for (uint32_t r = H; r < n; ++r) if (visits[r] > 0 && !mine(r)) cand.push_back(r);
-  const uint64_t want = std::min<uint64_t>(static_cast<uint64_t>(n) * ratio_pct / 100, cand.size());
+  for (uint32_t p = 0; p < ix->world; ++p) {
+    if (p == ix->rank) continue;
+    for (uint32_t r = ix->part_begin[p]; r < ix->part_begin[p] + ix->part_rows[p]; ++r) if (visits[r] > 0) cand.push_back(r);
+  }
+  const uint64_t want = std::min<uint64_t>(static_cast<uint64_t>(ix->n) * ratio_pct / 100, cand.size());
   auto hotter = [&](uint32_t a, uint32_t b) { return visits[a] != visits[b] ? visits[a] > visits[b] : a < b; };
   if (want < cand.size()) std::nth_element(cand.begin(), cand.begin() + want, cand.end(), hotter);
   cand.resize(want);
   std::sort(cand.begin(), cand.end());  // slots in row order: slot = prefix + popc(bits below)
   if (halo_rows) *halo_rows = want;
   if (want == 0) return SHN_OK;
-  const size_t words = (static_cast<size_t>(n - H) + 31) / 32;
+  const size_t words = (static_cast<size_t>(ids) + 31) / 32;
   std::vector<uint2> dir(words, make_uint2(0u, 0u));
-  for (uint32_t r : cand) dir[(r - H) >> 5].x |= 1u << ((r - H) & 31u);
+  for (uint32_t r : cand) dir[r >> 5].x |= 1u << (r & 31u);
   uint32_t run = 0;
   for (size_t w = 0; w < words; ++w) { dir[w].y = run; run += static_cast<uint32_t>(__builtin_popcount(dir[w].x)); }
-  const size_t row_bytes = static_cast<size_t>(ix->row_f4) * 16, m0 = 2ull * ix->m;
+  const size_t row_bytes = static_cast<size_t>(ix->row_f4) * 16, list_bytes = 2ull * ix->m * sizeof(uint32_t);
+  const char* why = "";
+  // the copies go behind the shares, in the same two address ranges: halo slot s is flat id n_ids + s
+  if (vmm_create(ix->halo_vec_blk, want * row_bytes, ix->gpu, &why) != cudaSuccess ||
+      vmm_create(ix->halo_l0_blk, want * list_bytes, ix->gpu, &why) != cudaSuccess ||
+      vmm_place(ix->vec_space, ids * row_bytes, ix->halo_vec_blk.size, ix->halo_vec_blk.handle, ix->gpu, &why) != cudaSuccess) {
+    vmm_drop(ix->halo_vec_blk); vmm_drop(ix->halo_l0_blk);
+    return fail(SHN_ERR_CUDA, "allocating the halo (%llu rows): %s failed", static_cast<unsigned long long>(want), why);
+  }
+  if (vmm_place(ix->l0_space, ids * list_bytes, ix->halo_l0_blk.size, ix->halo_l0_blk.handle, ix->gpu, &why) != cudaSuccess) {
+    vmm_unplace(ix->vec_space, ids * row_bytes, ix->halo_vec_blk.size);
+    vmm_drop(ix->halo_vec_blk); vmm_drop(ix->halo_l0_blk);
+    return fail(SHN_ERR_CUDA, "mapping the halo: %s failed", why);
+  }
   uint32_t* d_rows = nullptr;
   uint2* d_dir = nullptr;
-  float4* d_vec = nullptr;
-  uint32_t* d_l0 = nullptr;
   cudaError_t e = cudaMalloc(&d_rows, want * sizeof(uint32_t));
   if (e == cudaSuccess) e = cudaMalloc(&d_dir, words * sizeof(uint2));
-  if (e == cudaSuccess) e = cudaMalloc(&d_vec, want * row_bytes);
-  if (e == cudaSuccess) e = cudaMalloc(&d_l0, want * m0 * sizeof(uint32_t));
   if (e == cudaSuccess) e = cudaMemcpyAsync(d_rows, cand.data(), want * sizeof(uint32_t), cudaMemcpyHostToDevice, ix->stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(d_dir, dir.data(), words * sizeof(uint2), cudaMemcpyHostToDevice, ix->stream);
-  if (e == cudaSuccess) e = halo_gather(ix->view(), d_rows, static_cast<uint32_t>(want), d_vec, d_l0, ix->stream);
+  if (e == cudaSuccess) e = halo_gather(ix->view(), d_rows, static_cast<uint32_t>(want), ix->d_vec + static_cast<size_t>(ids) * ix->row_f4,
+                                        ix->d_l0 + static_cast<size_t>(ids) * 2 * ix->m, ix->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(ix->stream);
   cudaFree(d_rows);
   if (e != cudaSuccess) {
-    cudaFree(d_dir); cudaFree(d_vec); cudaFree(d_l0);
+    cudaFree(d_dir);
+    vmm_unplace(ix->vec_space, ids * row_bytes, ix->halo_vec_blk.size); vmm_unplace(ix->l0_space, ids * list_bytes, ix->halo_l0_blk.size);
+    vmm_drop(ix->halo_vec_blk); vmm_drop(ix->halo_l0_blk);
     return fail(SHN_ERR_CUDA, "building the halo (%llu rows): %s", static_cast<unsigned long long>(want), cudaGetErrorString(e));
   }
-  ix->d_halo_dir = d_dir; ix->d_halo_vec = d_vec; ix->d_halo_l0 = d_l0; ix->halo = static_cast<uint32_t>(want);
-  ix->hbm_bytes += want * (row_bytes + m0 * 4) + words * sizeof(uint2);
+  ix->d_halo_dir = d_dir; ix->halo = static_cast<uint32_t>(want);
+  ix->hbm_bytes += ix->halo_vec_blk.size + ix->halo_l0_blk.size + words * sizeof(uint2);
   return SHN_OK;
 }
 
@@ -643,32 +680,47 @@ int shn_index_partition(shn_index** out, const shn_index* full, int rank, int wo
     for (uint64_t i = 0; i < want; ++i) is_hot[cand[i]] = 1;
     hot += want;
   }
-  std::vector<uint32_t> new_of_old(n);
   const uint32_t H = static_cast<uint32_t>(hot);
-  const uint32_t cold = n - H;
-  uint32_t own = 0, begins[9];
-  for (auto& b : begins) b = kInvalid;
-  if (d_owner) {  // clustered placement: [hot | rows of GPU 0 | rows of GPU 1 | ...], old order kept inside each range
-    std::vector<uint8_t> owner(n);
+  const size_t row_bytes = static_cast<size_t>(full->row_f4) * 16, m0 = 2ull * full->m, list_bytes = m0 * sizeof(uint32_t);
+  // flat numbering (graph.h): every piece starts on a multiple of `align` rows, so that it starts on an allocation granule in
+  // both address ranges
+  size_t gran = 0;
+  {
+    const char* why = "";
+    if (vmm_granularity(full->gpu, &gran, &why) != cudaSuccess) return fail(SHN_ERR_CUDA, "%s failed", why);
+  }
+  auto gcd = [](size_t a, size_t b) { while (b) { const size_t t = a % b; a = b; b = t; } return a; };
+  const size_t align = std::max(gran / gcd(gran, row_bytes), gran / gcd(gran, list_bytes));
+  auto up = [&](uint64_t v) { return (v + align - 1) / align * align; };
+  // owner of every cold row: the placement (k-means cluster), or round-robin as the reference scatters nodes over the
+  // memory nodes (src/compute_thread.hh:57)
+  std::vector<uint8_t> owner(n);
+  if (d_owner) {
     CU(cudaMemcpy(owner.data(), d_owner, n, cudaMemcpyDeviceToHost));
-    std::vector<uint32_t> next(world + 1, 0);
-    for (uint32_t r = 0; r < n; ++r) {
-      if (is_hot[r]) continue;
-      if (owner[r] >= world) return fail(SHN_ERR_ARG, "owner[%u] = %u is not a rank below %d", r, owner[r], world);
-      ++next[owner[r] + 1];
-    }
-    begins[0] = H;
-    for (int g = 0; g < world; ++g) begins[g + 1] = begins[g] + next[g + 1];
-    own = next[rank + 1];
-    std::vector<uint32_t> cursor(begins, begins + world);
+  } else {
+    uint32_t cold = 0;
+    for (uint32_t r = 0; r < n; ++r) if (!is_hot[r]) owner[r] = static_cast<uint8_t>(cold++ % world);
+  }
+  uint64_t rows_of[8] = {0};
+  for (uint32_t r = 0; r < n; ++r) {
+    if (is_hot[r]) continue;
+    if (owner[r] >= world) return fail(SHN_ERR_ARG, "owner[%u] = %u is not a rank below %d", r, owner[r], world);
+    ++rows_of[owner[r]];
+  }
+  uint64_t begins[9];
+  begins[0] = up(std::max<uint64_t>(H, 1));
+  for (int g = 0; g < world; ++g) begins[g + 1] = begins[g] + up(std::max<uint64_t>(rows_of[g], 1));
+  const uint64_t n_flat = begins[world];
+  const uint64_t halo_cap = up(n);
+  if (n_flat + halo_cap >= (1ull << 31)) return fail(SHN_ERR_ARG, "the flat id space of the partition exceeds 2^31 - 1");
+  std::vector<uint32_t> new_of_old(n);
+  {
+    std::vector<uint32_t> cursor(world);
+    for (int g = 0; g < world; ++g) cursor[g] = static_cast<uint32_t>(begins[g]);
     uint32_t next_hot = 0;
     for (uint32_t r = 0; r < n; ++r) new_of_old[r] = is_hot[r] ? next_hot++ : cursor[owner[r]]++;
-    for (int g = world + 1; g < 9; ++g) begins[g] = kInvalid;
-  } else {        // the reference's policy: uniform scatter (compute_thread.hh:57), here round-robin over the cold rows
-    uint32_t next_hot = 0, next_cold = H;
-    for (uint32_t r = 0; r < n; ++r) new_of_old[r] = is_hot[r] ? next_hot++ : next_cold++;
-    own = cold > static_cast<uint32_t>(rank) ? (cold - rank + world - 1) / world : 0;
   }
+  const uint32_t own = static_cast<uint32_t>(rows_of[rank]);
 
   shn_index* ix = nullptr;
   int rc = new_handle(&ix, full->gpu, full->metric);
@@ -678,41 +730,54 @@ int shn_index_partition(shn_index** out, const shn_index* full, int rank, int wo
   ix->n = n; ix->dim = full->dim; ix->m = full->m; ix->row_f4 = full->row_f4; ix->n_up = full->n_up; ix->max_level = full->max_level;
   ix->max_level_of_ep = full->max_level_of_ep; ix->ep_row = new_of_old[full->ep_row];
   ix->hot = H; ix->world = world; ix->rank = rank; ix->own = own; ix->attached = 1;
-  ix->clustered = d_owner ? 1u : 0u;
-  for (int i = 0; i < 9; ++i) ix->part_begin[i] = d_owner ? begins[i] : 0u;
+  ix->n_ids = static_cast<uint32_t>(n_flat); ix->row_align = align;
+  for (int i = 0; i < 9; ++i) ix->part_begin[i] = i <= world ? static_cast<uint32_t>(begins[i]) : kInvalid;
+  for (int i = 0; i < 8; ++i) ix->part_rows[i] = i < world ? static_cast<uint32_t>(rows_of[i]) : 0u;
   ix->warps_per_sm = full->warps_per_sm; ix->vis_cap = full->vis_cap; ix->dump_bytes = full->dump_bytes;
-  const size_t row_bytes = static_cast<size_t>(ix->row_f4) * 16, m0 = 2ull * ix->m;
-  uint32_t *d_new_of_old = nullptr, *d_old_of_new = nullptr;
-  CUB(cudaMalloc(&d_new_of_old, n * sizeof(uint32_t)));
-  CUB(cudaMalloc(&d_old_of_new, n * sizeof(uint32_t)));
-  CUB(cudaMemcpy(d_new_of_old, new_of_old.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice));
-  CUB(cudaMalloc(&ix->d_vec, std::max<size_t>(H, 1) * row_bytes));
-  CUB(cudaMalloc(&ix->d_l0, std::max<size_t>(H, 1) * m0 * sizeof(uint32_t)));
-  CUB(cudaMalloc(&ix->d_up_base, std::max<size_t>(H, 1) * sizeof(uint32_t)));
-  CUB(cudaMalloc(&ix->d_up, std::max<size_t>(ix->n_up, 1) * ix->m * sizeof(uint32_t)));
-  CUB(cudaMalloc(&ix->d_ext_id, n * sizeof(uint32_t)));
   {
     const char* why = "";
-    if (vmm_alloc(ix->own_vec_blk, std::max<size_t>(own, 1) * row_bytes, ix->gpu, &why) != cudaSuccess ||
-        vmm_alloc(ix->own_l0_blk, std::max<size_t>(own, 1) * m0 * sizeof(uint32_t), ix->gpu, &why) != cudaSuccess)
-      return bail(fail(SHN_ERR_CUDA, "allocating this GPU's share: %s failed", why));
-    ix->d_own_vec = static_cast<float4*>(ix->own_vec_blk.ptr);
-    ix->d_own_l0 = static_cast<uint32_t*>(ix->own_l0_blk.ptr);
+    if (vmm_reserve(ix->vec_space, (n_flat + halo_cap) * row_bytes, gran, &why) != cudaSuccess ||
+        vmm_reserve(ix->l0_space, (n_flat + halo_cap) * list_bytes, gran, &why) != cudaSuccess)
+      return bail(fail(SHN_ERR_CUDA, "reserving the partition's address ranges: %s failed", why));
+    ix->d_vec = static_cast<float4*>(ix->vec_space.base);
+    ix->d_l0 = static_cast<uint32_t*>(ix->l0_space.base);
+    if (vmm_create(ix->hot_vec_blk, begins[0] * row_bytes, ix->gpu, &why) != cudaSuccess ||
+        vmm_create(ix->hot_l0_blk, begins[0] * list_bytes, ix->gpu, &why) != cudaSuccess ||
+        vmm_create(ix->own_vec_blk, up(std::max<uint64_t>(own, 1)) * row_bytes, ix->gpu, &why) != cudaSuccess ||
+        vmm_create(ix->own_l0_blk, up(std::max<uint64_t>(own, 1)) * list_bytes, ix->gpu, &why) != cudaSuccess)
+      return bail(fail(SHN_ERR_CUDA, "allocating the hot set and this GPU's share: %s failed", why));
+    if (vmm_place(ix->vec_space, 0, ix->hot_vec_blk.size, ix->hot_vec_blk.handle, ix->gpu, &why) != cudaSuccess ||
+        vmm_place(ix->l0_space, 0, ix->hot_l0_blk.size, ix->hot_l0_blk.handle, ix->gpu, &why) != cudaSuccess ||
+        vmm_place(ix->vec_space, begins[rank] * row_bytes, ix->own_vec_blk.size, ix->own_vec_blk.handle, ix->gpu, &why) != cudaSuccess ||
+        vmm_place(ix->l0_space, begins[rank] * list_bytes, ix->own_l0_blk.size, ix->own_l0_blk.handle, ix->gpu, &why) != cudaSuccess)
+      return bail(fail(SHN_ERR_CUDA, "mapping the hot set and this GPU's share: %s failed", why));
   }
-  ix->hbm_bytes = H * (row_bytes + m0 * 4 + 4) + own * (row_bytes + m0 * 4) + n * 4ull + std::max<size_t>(ix->n_up, 1) * ix->m * 4;
+  uint32_t *d_new_of_old = nullptr, *d_old_of_new = nullptr;
+  CUB(cudaMalloc(&d_new_of_old, n * sizeof(uint32_t)));
+  CUB(cudaMalloc(&d_old_of_new, n_flat * sizeof(uint32_t)));
+  CUB(cudaMemcpy(d_new_of_old, new_of_old.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  CUB(cudaMalloc(&ix->d_up_base, begins[0] * sizeof(uint32_t)));
+  CUB(cudaMalloc(&ix->d_up, std::max<size_t>(ix->n_up, 1) * ix->m * sizeof(uint32_t)));
+  CUB(cudaMalloc(&ix->d_ext_id, n_flat * sizeof(uint32_t)));
+  // the pads read as empty rows with empty lists
+  CUB(cudaMemsetAsync(ix->d_vec, 0, ix->hot_vec_blk.size, ix->stream));
+  CUB(cudaMemsetAsync(ix->d_l0, 0xFF, ix->hot_l0_blk.size, ix->stream));
+  CUB(cudaMemsetAsync(ix->d_vec + begins[rank] * ix->row_f4, 0, ix->own_vec_blk.size, ix->stream));
+  CUB(cudaMemsetAsync(ix->d_l0 + begins[rank] * m0, 0xFF, ix->own_l0_blk.size, ix->stream));
+  ix->hbm_bytes = ix->hot_vec_blk.size + ix->hot_l0_blk.size + ix->own_vec_blk.size + ix->own_l0_blk.size + begins[0] * 4ull +
+                  n_flat * 4ull + std::max<size_t>(ix->n_up, 1) * ix->m * 4;
   PartitionJob job;
-  job.n = n; job.hot = H; job.own = own; job.rank = d_owner ? 0 : rank; job.world = d_owner ? 1 : world;
-  job.own_first = d_owner ? begins[rank] : H + rank; job.row_f4 = ix->row_f4; job.m = ix->m; job.m0 = 2 * ix->m;
+  job.n = n; job.n_flat = static_cast<uint32_t>(n_flat); job.hot = H; job.own_first = static_cast<uint32_t>(begins[rank]); job.own = own;
+  job.row_f4 = ix->row_f4; job.m = ix->m; job.m0 = 2 * ix->m;
   job.n_up = ix->n_up; job.new_of_old = d_new_of_old; job.old_of_new = d_old_of_new;
   job.src_vec = full->d_vec; job.src_l0 = full->d_l0; job.src_up_base = full->d_up_base; job.src_up = full->d_up; job.src_ext_id = full->d_ext_id;
-  job.hot_vec = ix->d_vec; job.own_vec = ix->d_own_vec; job.hot_l0 = ix->d_l0; job.own_l0 = ix->d_own_l0;
+  job.hot_vec = ix->d_vec; job.own_vec = ix->d_vec + begins[rank] * ix->row_f4;
+  job.hot_l0 = ix->d_l0; job.own_l0 = ix->d_l0 + begins[rank] * m0;
   job.hot_up_base = ix->d_up_base; job.up = ix->d_up; job.ext_id = ix->d_ext_id;
   cudaError_t e = partition_arrays(job, ix->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(ix->stream);
   cudaFree(d_new_of_old); cudaFree(d_old_of_new);
   if (e != cudaSuccess) return bail(fail(SHN_ERR_CUDA, "partition_arrays: %s", cudaGetErrorString(e)));
-  ix->part_vec[rank] = ix->d_own_vec;
-  ix->part_l0[rank] = ix->d_own_l0;
 #undef CUB
   *out = ix;
   return SHN_OK;
@@ -846,33 +911,43 @@ int shn_index_partition_export(const shn_index* ix, int* fds, uint64_t* sizes, u
       return fail(SHN_ERR_CUDA, "exporting the share: %s failed", why);
   }
   if (sizes) { sizes[0] = ix->own_vec_blk.size; sizes[1] = ix->own_l0_blk.size; }
-  if (raw_ptrs) { raw_ptrs[0] = reinterpret_cast<uint64_t>(ix->d_own_vec); raw_ptrs[1] = reinterpret_cast<uint64_t>(ix->d_own_l0); }
+  // inside one process the share travels as the handle that owns it (its allocations are mapped a second time, into the
+  // attaching handle's address ranges)
+  if (raw_ptrs) { raw_ptrs[0] = reinterpret_cast<uint64_t>(ix); raw_ptrs[1] = ~reinterpret_cast<uint64_t>(ix); }
   return SHN_OK;
 }
 
 int shn_index_partition_attach(shn_index* ix, int peer, const int* fds, const uint64_t* sizes, const uint64_t* raw_ptrs) {
   if (!ix || ix->world < 2) return fail(SHN_ERR_STATE, "not a partitioned handle");
   if (peer < 0 || peer >= static_cast<int>(ix->world) || peer == static_cast<int>(ix->rank)) return fail(SHN_ERR_ARG, "bad peer rank %d", peer);
-  if (!raw_ptrs && !(fds && sizes)) return fail(SHN_ERR_ARG, "need file descriptors with sizes, or raw pointers");
+  if (!raw_ptrs && !(fds && sizes)) return fail(SHN_ERR_ARG, "need file descriptors with sizes, or the in-process tokens of shn_index_partition_export");
+  if (ix->peer_placed[peer]) return fail(SHN_ERR_STATE, "rank %d is already attached", peer);
   CU(cudaSetDevice(ix->gpu));
-  void *vp = nullptr, *lp = nullptr;
-  if (raw_ptrs) {  // same process (tests, single-process multi-GPU): the pointers are usable as they are
-    vp = reinterpret_cast<void*>(raw_ptrs[0]); lp = reinterpret_cast<void*>(raw_ptrs[1]);
-    cudaPointerAttributes attr;
-    if (cudaPointerGetAttributes(&attr, vp) == cudaSuccess && attr.type == cudaMemoryTypeDevice && attr.device != ix->gpu) {
-      const cudaError_t pe = cudaDeviceEnablePeerAccess(attr.device, 0);  // the share lives on another GPU of this process
-      if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) return fail(SHN_ERR_CUDA, "peer access to GPU %d: %s", attr.device, cudaGetErrorString(pe));
-      cudaGetLastError();
-    }
-  } else {         // another process: map its physical allocations into this GPU's address space (loads go over NVLink)
-    const char* why = "";
-    if (vmm_import_fd(ix->peer_vec_blk[peer], fds[0], sizes[0], ix->gpu, &why) != cudaSuccess ||
-        vmm_import_fd(ix->peer_l0_blk[peer], fds[1], sizes[1], ix->gpu, &why) != cudaSuccess)
-      return fail(SHN_ERR_CUDA, "mapping the share of rank %d: %s failed", peer, why);
-    vp = ix->peer_vec_blk[peer].ptr; lp = ix->peer_l0_blk[peer].ptr;
+  const size_t row_bytes = static_cast<size_t>(ix->row_f4) * 16, list_bytes = 2ull * ix->m * sizeof(uint32_t);
+  const size_t room_rows = ix->part_begin[peer + 1] - ix->part_begin[peer];
+  unsigned long long hv = 0, hl = 0;
+  size_t sv = 0, sl = 0;
+  const char* why = "";
+  if (raw_ptrs) {  // same process (tests, shn_group): the peer's handle itself
+    const shn_index* other = reinterpret_cast<const shn_index*>(raw_ptrs[0]);
+    if (!other || raw_ptrs[1] != ~raw_ptrs[0] || other->world != ix->world || static_cast<int>(other->rank) != peer || other->n_ids != ix->n_ids ||
+        other->hot != ix->hot || other->part_begin[peer] != ix->part_begin[peer])
+      return fail(SHN_ERR_ARG, "the token is not rank %d of this partitioned index", peer);
+    hv = other->own_vec_blk.handle; hl = other->own_l0_blk.handle; sv = other->own_vec_blk.size; sl = other->own_l0_blk.size;
+  } else {         // another process: import its physical allocations (loads will go over NVLink)
+    if (vmm_import_handle(ix->peer_vec_blk[peer], fds[0], sizes[0], &why) != cudaSuccess ||
+        vmm_import_handle(ix->peer_l0_blk[peer], fds[1], sizes[1], &why) != cudaSuccess)
+      return fail(SHN_ERR_CUDA, "importing the share of rank %d: %s failed", peer, why);
+    hv = ix->peer_vec_blk[peer].handle; hl = ix->peer_l0_blk[peer].handle; sv = sizes[0]; sl = sizes[1];
   }
-  ix->part_vec[peer] = static_cast<const float4*>(vp);
-  ix->part_l0[peer] = static_cast<const uint32_t*>(lp);
+  if (sv > room_rows * row_bytes || sl > room_rows * list_bytes) return fail(SHN_ERR_ARG, "the share of rank %d does not fit its place in the id space (another partitioning?)", peer);
+  if (vmm_place(ix->vec_space, ix->part_begin[peer] * row_bytes, sv, hv, ix->gpu, &why) != cudaSuccess)
+    return fail(SHN_ERR_CUDA, "mapping the share of rank %d: %s failed", peer, why);
+  if (vmm_place(ix->l0_space, ix->part_begin[peer] * list_bytes, sl, hl, ix->gpu, &why) != cudaSuccess) {
+    vmm_unplace(ix->vec_space, ix->part_begin[peer] * row_bytes, sv);
+    return fail(SHN_ERR_CUDA, "mapping the share of rank %d: %s failed", peer, why);
+  }
+  ix->peer_placed[peer] = true; ix->peer_vec_bytes[peer] = sv; ix->peer_l0_bytes[peer] = sl;
   ++ix->attached;
   return SHN_OK;
 }
@@ -907,14 +982,11 @@ int shn_debug_select_neighbors(shn_index* ix, const uint32_t* cand_rows, const f
 // Diagnostic (not in include/shn.h): bandwidth of random whole-row reads from partition `part` as this GPU sees it.
 double shn_debug_partition_gather_gbs(shn_index* ix, int part) {
   if (!ix || ix->world < 2 || part < 0 || part >= static_cast<int>(ix->world)) return -1.0;
+  if (part != static_cast<int>(ix->rank) && !ix->peer_placed[part]) return -1.0;
   cudaSetDevice(ix->gpu);
-  const float4* ptr = ix->part_vec[part];
-  if (!ptr) return -1.0;
-  const uint32_t cold = ix->n - ix->hot;
-  const uint32_t rows = ix->clustered ? ix->part_begin[part + 1] - ix->part_begin[part]
-                                      : (cold > static_cast<uint32_t>(part) ? (cold - part + ix->world - 1) / ix->world : 0);
+  const uint32_t rows = ix->part_rows[part];
   double gbs = -1.0;
-  if (rows == 0 || probe_gather(ptr, rows, ix->row_f4, &gbs, ix->stream) != cudaSuccess) return -1.0;
+  if (rows == 0 || probe_gather(ix->d_vec + static_cast<size_t>(ix->part_begin[part]) * ix->row_f4, rows, ix->row_f4, &gbs, ix->stream) != cudaSuccess) return -1.0;
   return gbs;
 }
 

@@ -68,11 +68,14 @@ cudaError_t rows_from_layout(const float* d_src, float* d_dst, uint64_t n, uint3
 
 // ---- partitioning (partition.cu)
 struct PartitionJob {
-  uint32_t n = 0, hot = 0, own = 0, rank = 0, world = 1, row_f4 = 0, m = 0, m0 = 0;
-  uint32_t own_first = 0;  // new id of this GPU's first own row; its rows are own_first + i * world
+  uint32_t n = 0;        // rows of the source index
+  uint32_t n_flat = 0;   // size of the flat id space (graph.h)
+  uint32_t hot = 0;      // flat ids [0, hot): the replicated hot set
+  uint32_t own_first = 0, own = 0;  // flat ids of this GPU's share
+  uint32_t row_f4 = 0, m = 0, m0 = 0;
   uint64_t n_up = 0;
   const uint32_t* new_of_old = nullptr;  // [n] device
-  uint32_t* old_of_new = nullptr;        // [n] device scratch
+  uint32_t* old_of_new = nullptr;        // [n_flat] device scratch
   const float4* src_vec = nullptr;
   const uint32_t *src_l0 = nullptr, *src_up_base = nullptr, *src_up = nullptr, *src_ext_id = nullptr;
   float4 *hot_vec = nullptr, *own_vec = nullptr;

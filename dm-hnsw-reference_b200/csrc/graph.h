@@ -71,88 +71,66 @@ void emit_dumps(const HostGraph& g, int n_parts, void* const* dumps);
 
 // Device view, passed to kernels by value.
 //
-// One GPU: every row is in vec / l0 (hot == n, world == 1).  Partitioned over `world` GPUs (partition.cu): rows are
-// renumbered so that the replicated hot set comes first — rows [0, hot) (all nodes with level > 0 plus the most visited
-// level-0 nodes) live in every GPU's vec / l0, the HBM-resident stand-in for the reference's compute-node cache
-// (src/cache/cache.hh) — and row r >= hot lives on GPU (r - hot) % world at local index (r - hot) / world, as the
-// reference scatters nodes over memory nodes (src/compute_thread.hh:57); part_vec / part_l0 are device tables of the
-// `world` base pointers (peer-mapped for the other GPUs: what was an RDMA READ is a load over NVLink).
+// One GPU: every row is in vec / l0 (hot == n, world == 1).
+//
+// Partitioned over `world` GPUs (capi.cu shn_index_partition): rows are renumbered ("flat numbering")
+//     [ hot set | pad | share of GPU 0 | pad | share of GPU 1 | pad | ... ]            ids < n_flat
+//     [ halo of THIS GPU ]                                                              ids >= n_flat, never stored in a list
+// and vec / l0 are ONE address range per GPU in which every piece is a separate physical allocation (vmm.h VmmSpace): the
+// hot set — all nodes with level > 0 plus the most visited level-0 nodes, the HBM-resident stand-in for the reference's
+// compute-node cache (src/cache/cache.hh) — is this GPU's own copy, the GPU's share is local, a peer's share is the
+// peer's physical memory mapped here (what was an RDMA READ, src/rdma/rdma_reads.hh, is a load over NVLink), and the pads
+// make every piece start on an allocation-granule boundary.  A row therefore lives at vec + row * row_f4 wherever it
+// is; the MMU does what a placement lookup would otherwise do in the instruction stream.  Nodes are placed by owner
+// (shn_placement_fit: k-means cluster; or round-robin as the reference scatters them, src/compute_thread.hh:57).
+//
+// Halo (shn_index_partition_build_halo): local copies of the peer-owned rows THIS GPU's queries read most — with query
+// routing a GPU's queries stay near its own cluster, and what they read remotely are the same border rows again and
+// again.  The copies sit behind the shares in the same address range (ids n_flat + slot); the directory holds one
+// {bits, prefix} pair per 32 flat ids (bit i: row 32 w + i is in the halo; prefix: halo rows before word w), n/4 bytes in
+// all, so it stays in L2, and only rows of a peer's share ever consult it.
 struct DeviceGraph {
   const float4* vec;
   const uint32_t* l0;
   const uint32_t* up_base;   // rows < hot only (every node with level > 0 is hot)
   const uint32_t* up;
   const uint32_t* ext_id;
-  uint32_t n, dim, m, m0;
-  uint32_t row_f4;    // row stride of vec in float4
+  uint32_t n, dim, m, m0;    // n: size of the id space (partitions: n_flat)
+  uint32_t row_f4;           // row stride of vec in float4
   uint32_t ep_row, ep_level;
   uint32_t hot, world, rank;
-  uint32_t clustered;       // 0: row r >= hot lives on GPU (r-hot) % world; 1: GPU p owns rows [part_begin[p], part_begin[p+1])
-  uint32_t part_begin[9];   // clustered placement (placement.cu); entries beyond `world` are 0xFFFFFFFF
-  const float4* part_vec[8];   // base of every GPU's share as this GPU addresses it (kernel parameter = constant bank)
-  const uint32_t* part_l0[8];
-  uint32_t* visit_count;  // optional [n]: +1 per level-0 distance computation (warm-up pass that picks the hot set)
-  // Halo (shn_index_partition_build_halo): local copies of the peer-owned rows THIS GPU's queries read most — with query
-  // routing a GPU's queries stay near its own cluster, and what they read remotely are the same border rows again and
-  // again.  The directory holds one {bits, prefix} pair per 32 rows >= hot (bit i: row hot + 32 w + i is in the halo;
-  // prefix: halo rows before word w), n/4 bytes in all, so it stays in L2; a row's slot is prefix + popc(bits below).
+  uint32_t own_lo, own_hi;   // this GPU's share: flat ids [own_lo, own_hi)
+  uint32_t halo_first;       // flat id of halo slot 0 (= n_flat)
   const uint2* halo_dir;     // nullptr = no halo
-  const float4* halo_vec;    // [halo][row_f4]
-  const uint32_t* halo_l0;   // [halo][2m]
+  uint32_t* visit_count;     // optional [n]: +1 per level-0 distance computation (warm-up passes that pick hot set and halo)
 };
 
 #ifdef __CUDACC__
-// owner GPU and local index of a row that is not in the replicated hot set
-__device__ __forceinline__ void locate_row(const DeviceGraph& g, uint32_t row, uint32_t& part, uint32_t& idx) {
-  if (g.clustered) {
-    part = 0;
-    uint32_t begin = g.part_begin[0];
-#pragma unroll
-    for (int j = 1; j < 8; ++j) {
-      if (row >= g.part_begin[j]) { part = j; begin = g.part_begin[j]; }
-    }
-    idx = row - begin;
-  } else {
-    const uint32_t o = row - g.hot;
-    part = o % g.world;
-    idx = o / g.world;
+// Where a level-0 row is read from.
+enum RowClass : uint32_t { kRowHot = 0, kRowOwn = 1, kRowHalo = 2, kRowPeer = 3 };
+// The id under which `row` is read on this GPU: itself, or its halo copy.  PART = false: the handle holds every row (one
+// GPU, or the builder) and nothing of this is in the instruction stream.
+template <bool PART>
+__device__ __forceinline__ uint32_t read_id(const DeviceGraph& g, uint32_t row, uint32_t& cls) {
+  if (!PART || row < g.hot) { cls = kRowHot; return row; }
+  if (row >= g.own_lo && row < g.own_hi) { cls = kRowOwn; return row; }
+  cls = kRowPeer;
+  if (g.halo_dir) {
+    const uint2 e = __ldg(g.halo_dir + (row >> 5));
+    const uint32_t bit = 1u << (row & 31u);
+    if (e.x & bit) { cls = kRowHalo; return g.halo_first + e.y + __popc(e.x & (bit - 1u)); }
   }
+  return row;
 }
-// Where a row lives, as this GPU sees it: loc < 8 = the share of GPU loc (own or peer-mapped), kLocHot = the replicated
-// hot set, kLocHalo = this GPU's halo; idx = the row's index there.
-constexpr uint32_t kLocHot = 8, kLocHalo = 9;
-__device__ __forceinline__ void resolve_row(const DeviceGraph& g, uint32_t row, uint32_t& loc, uint32_t& idx) {
-  if (row < g.hot) { loc = kLocHot; idx = row; return; }
-  locate_row(g, row, loc, idx);
-  if (loc != g.rank && g.halo_dir) {
-    const uint32_t o = row - g.hot;
-    const uint2 e = __ldg(g.halo_dir + (o >> 5));
-    const uint32_t bit = 1u << (o & 31u);
-    if (e.x & bit) { loc = kLocHalo; idx = e.y + __popc(e.x & (bit - 1u)); }
-  }
-}
-__device__ __forceinline__ const float4* vec_at(const DeviceGraph& g, uint32_t loc, uint32_t idx) {
-  const float4* base = loc == kLocHot ? g.vec : (loc == kLocHalo ? g.halo_vec : g.part_vec[loc]);
-  return base + static_cast<size_t>(idx) * g.row_f4;
-}
-__device__ __forceinline__ const uint32_t* l0_at(const DeviceGraph& g, uint32_t loc, uint32_t idx) {
-  const uint32_t* base = loc == kLocHot ? g.l0 : (loc == kLocHalo ? g.halo_l0 : g.part_l0[loc]);
-  return base + static_cast<size_t>(idx) * g.m0;
-}
-// PART = false: the handle holds every row (one GPU, or the builder): no placement test in the instruction stream
 template <bool PART>
 __device__ __forceinline__ const float4* vec_row(const DeviceGraph& g, uint32_t row) {
-  if (!PART || row < g.hot) return g.vec + static_cast<size_t>(row) * g.row_f4;
-  uint32_t loc, idx;
-  resolve_row(g, row, loc, idx);
-  return vec_at(g, loc, idx);
+  uint32_t cls;
+  return g.vec + static_cast<size_t>(read_id<PART>(g, row, cls)) * g.row_f4;
 }
 template <bool PART>
 __device__ __forceinline__ const uint32_t* l0_row(const DeviceGraph& g, uint32_t row) {
-  if (!PART || row < g.hot) return g.l0 + static_cast<size_t>(row) * g.m0;
-  uint32_t loc, idx;
-  resolve_row(g, row, loc, idx);
-  return l0_at(g, loc, idx);
+  uint32_t cls;
+  return g.l0 + static_cast<size_t>(read_id<PART>(g, row, cls)) * g.m0;
 }
 #endif
 

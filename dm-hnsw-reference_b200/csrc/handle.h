@@ -75,32 +75,33 @@ struct shn_index {
   int warps_per_sm = 0;
   uint32_t vis_cap = 0;
   shn_stats build_stats{};
-  // partitioned handle (shn_index_partition): d_vec / d_l0 / d_up_base hold the replicated hot set
-  uint32_t hot = 0, world = 1, rank = 0, own = 0, attached = 1, clustered = 0;
-  uint32_t part_begin[9] = {0};
-  float4* d_own_vec = nullptr;
-  uint32_t* d_own_l0 = nullptr;
-  const float4* part_vec[8] = {nullptr};   // the shares as this GPU addresses them (own, or peer-mapped); travel to the
-  const uint32_t* part_l0[8] = {nullptr};  // kernels inside DeviceGraph, i.e. in the constant bank
+  // partitioned handle (shn_index_partition; graph.h "flat numbering"): d_vec / d_l0 are the bases of two address ranges
+  // into which the hot set, this GPU's share, the peers' shares and the halo are mapped; n_ids = size of the id space
+  uint32_t hot = 0, world = 1, rank = 0, own = 0, attached = 1;
+  uint32_t n_ids = 0;                    // flat ids in use (n for a full index)
+  uint32_t part_begin[9] = {0};          // share p = flat ids [part_begin[p], part_begin[p] + part_rows[p])
+  uint32_t part_rows[8] = {0};
+  size_t row_align = 0;                  // pieces start at multiples of this many rows
+  shn::VmmSpace vec_space, l0_space;
+  shn::VmmBlock hot_vec_blk, hot_l0_blk;      // replicated hot set (this GPU's copy)
   shn::VmmBlock own_vec_blk, own_l0_blk;      // this GPU's share (exportable as POSIX fds)
-  shn::VmmBlock peer_vec_blk[8], peer_l0_blk[8];  // shares of other processes mapped here
-  uint32_t* d_visits = nullptr;          // [n] when visit counting is on
-  uint2* d_halo_dir = nullptr;           // halo (graph.h): directory, rows, lists; halo = number of rows
-  float4* d_halo_vec = nullptr;
-  uint32_t* d_halo_l0 = nullptr;
+  shn::VmmBlock peer_vec_blk[8], peer_l0_blk[8];  // shares of other processes imported here (handles of this process are mapped directly)
+  bool peer_placed[8] = {false};
+  size_t peer_vec_bytes[8] = {0}, peer_l0_bytes[8] = {0};
+  shn::VmmBlock halo_vec_blk, halo_l0_blk;    // halo (graph.h): local copies of peer-owned rows, mapped behind the shares
+  uint2* d_halo_dir = nullptr;
   uint32_t halo = 0;
+  uint32_t* d_visits = nullptr;          // [n_ids] when visit counting is on
   bool built = false;
 
   shn::DeviceGraph view() const {
     shn::DeviceGraph g;
     g.vec = d_vec; g.l0 = d_l0; g.up_base = d_up_base; g.up = d_up; g.ext_id = d_ext_id;
-    g.n = n; g.dim = dim; g.m = m; g.m0 = 2 * m; g.row_f4 = row_f4; g.ep_row = ep_row; g.ep_level = max_level_of_ep;
+    g.n = world > 1 ? n_ids : n; g.dim = dim; g.m = m; g.m0 = 2 * m; g.row_f4 = row_f4; g.ep_row = ep_row; g.ep_level = max_level_of_ep;
     g.hot = world > 1 ? hot : n; g.world = world; g.rank = rank;
-    for (int i = 0; i < 8; ++i) { g.part_vec[i] = part_vec[i]; g.part_l0[i] = part_l0[i]; }
+    g.own_lo = part_begin[rank]; g.own_hi = part_begin[rank] + part_rows[rank];
+    g.halo_first = n_ids; g.halo_dir = d_halo_dir;
     g.visit_count = d_visits;
-    g.clustered = clustered;
-    g.halo_dir = d_halo_dir; g.halo_vec = d_halo_vec; g.halo_l0 = d_halo_l0;
-    for (int i = 0; i < 9; ++i) g.part_begin[i] = part_begin[i];
     return g;
   }
   uint32_t max_level_of_ep = 0;

@@ -1,5 +1,6 @@
-// partition.cu — split a full index (one GPU) into the share one GPU of `world` keeps (graph.h DeviceGraph):
-// rows are renumbered hot-set first; the hot rows are replicated, the others dealt round-robin to the GPUs.
+// partition.cu — split a full index (one GPU) into what one GPU of `world` keeps (graph.h DeviceGraph, flat numbering):
+// rows are renumbered [hot set | share 0 | share 1 | ...] with granule-aligned pieces; this GPU materialises the hot set
+// and its own share.
 #include "engine.h"
 
 namespace shn {
@@ -9,27 +10,29 @@ __global__ void invert_perm_kernel(const uint32_t* __restrict__ new_of_old, uint
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) old_of_new[new_of_old[i]] = i;
 }
 
-// dst[i] = src[old_of_new[first + i * step]], rows of row_f4 float4; a warp per destination row
+// dst[i] = src[old_of_new[first + i]], rows of row_f4 float4; a warp per destination row.  Flat ids nobody was given (the pads
+// between the pieces) stay zero.
 __global__ void gather_rows_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ old_of_new, uint32_t first,
-                                   uint32_t step, uint32_t count, uint32_t row_f4, float4* __restrict__ dst) {
+                                   uint32_t count, uint32_t row_f4, float4* __restrict__ dst) {
   const uint32_t warps = gridDim.x * (blockDim.x >> 5);
   const int lane = threadIdx.x & 31;
   for (uint32_t i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < count; i += warps) {
-    const uint32_t old = old_of_new[first + static_cast<uint64_t>(i) * step];
+    const uint32_t old = old_of_new[first + i];
+    if (old == kInvalid) continue;
     for (uint32_t f = lane; f < row_f4; f += 32) dst[static_cast<size_t>(i) * row_f4 + f] = src[static_cast<size_t>(old) * row_f4 + f];
   }
 }
 
-// dst[i][s] = remap(src[old_of_new[first + i*step]][s]); 0xFFFFFFFF stays
+// dst[i][s] = remap(src[old_of_new[first + i]][s]); 0xFFFFFFFF stays
 __global__ void gather_lists_kernel(const uint32_t* __restrict__ src, uint32_t width, const uint32_t* __restrict__ old_of_new,
-                                    const uint32_t* __restrict__ new_of_old, uint32_t first, uint32_t step, uint32_t count,
+                                    const uint32_t* __restrict__ new_of_old, uint32_t first, uint32_t count,
                                     uint32_t* __restrict__ dst) {
   const uint64_t total = static_cast<uint64_t>(count) * width;
   for (uint64_t t = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; t < total;
        t += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
     const uint32_t i = static_cast<uint32_t>(t / width), s = static_cast<uint32_t>(t % width);
-    const uint32_t old = old_of_new[first + static_cast<uint64_t>(i) * step];
-    const uint32_t nb = src[static_cast<size_t>(old) * width + s];
+    const uint32_t old = old_of_new[first + i];
+    const uint32_t nb = old == kInvalid ? kInvalid : src[static_cast<size_t>(old) * width + s];
     dst[t] = nb == kInvalid ? kInvalid : new_of_old[nb];
   }
 }
@@ -45,7 +48,10 @@ __global__ void remap_kernel(const uint32_t* __restrict__ src, const uint32_t* _
 
 __global__ void gather_u32_kernel(const uint32_t* __restrict__ src, const uint32_t* __restrict__ old_of_new, uint32_t count,
                                   uint32_t* __restrict__ dst) {
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) dst[i] = src[old_of_new[i]];
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+    const uint32_t old = old_of_new[i];
+    dst[i] = old == kInvalid ? kInvalid : src[old];
+  }
 }
 
 // diagnostic: random whole-row reads from one share (local or peer-mapped)
@@ -69,8 +75,8 @@ __global__ void halo_gather_kernel(const DeviceGraph g, const uint32_t* __restri
   const int lane = threadIdx.x & 31;
   for (uint32_t i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < count; i += warps) {
     const uint32_t row = rows[i];
-    const float4* v = vec_row<true>(g, row);
-    const uint32_t* l = l0_row<true>(g, row);
+    const float4* v = vec_row<false>(g, row);   // flat numbering: the row is where its id says, on whichever GPU
+    const uint32_t* l = l0_row<false>(g, row);
     for (uint32_t f = lane; f < g.row_f4; f += 32) dst_vec[static_cast<size_t>(i) * g.row_f4 + f] = v[f];
     for (uint32_t f = lane; f < g.m0; f += 32) dst_l0[static_cast<size_t>(i) * g.m0 + f] = l[f];
   }
@@ -83,18 +89,21 @@ inline int grid_for(uint64_t work, int threads) {
 }  // namespace
 
 cudaError_t partition_arrays(const PartitionJob& j, cudaStream_t s) {
-  const uint32_t n = j.n, hot = j.hot;
-  invert_perm_kernel<<<grid_for(n, 256), 256, 0, s>>>(j.new_of_old, j.old_of_new, n);
-  // replicated hot set
-  gather_rows_kernel<<<grid_for(static_cast<uint64_t>(hot) * 32, 256), 256, 0, s>>>(j.src_vec, j.old_of_new, 0, 1, hot, j.row_f4, j.hot_vec);
-  gather_lists_kernel<<<grid_for(static_cast<uint64_t>(hot) * j.m0, 256), 256, 0, s>>>(j.src_l0, j.m0, j.old_of_new, j.new_of_old, 0, 1, hot, j.hot_l0);
-  gather_u32_kernel<<<grid_for(hot, 256), 256, 0, s>>>(j.src_up_base, j.old_of_new, hot, j.hot_up_base);
+  cudaError_t e = cudaMemsetAsync(j.old_of_new, 0xFF, static_cast<size_t>(j.n_flat) * sizeof(uint32_t), s);
+  if (e != cudaSuccess) return e;
+  invert_perm_kernel<<<grid_for(j.n, 256), 256, 0, s>>>(j.new_of_old, j.old_of_new, j.n);
+  // replicated hot set: flat ids [0, hot)
+  if (j.hot) {
+    gather_rows_kernel<<<grid_for(static_cast<uint64_t>(j.hot) * 32, 256), 256, 0, s>>>(j.src_vec, j.old_of_new, 0, j.hot, j.row_f4, j.hot_vec);
+    gather_lists_kernel<<<grid_for(static_cast<uint64_t>(j.hot) * j.m0, 256), 256, 0, s>>>(j.src_l0, j.m0, j.old_of_new, j.new_of_old, 0, j.hot, j.hot_l0);
+    gather_u32_kernel<<<grid_for(j.hot, 256), 256, 0, s>>>(j.src_up_base, j.old_of_new, j.hot, j.hot_up_base);
+  }
   if (j.n_up) remap_kernel<<<grid_for(j.n_up * j.m, 256), 256, 0, s>>>(j.src_up, j.new_of_old, j.n_up * j.m, j.up);
-  gather_u32_kernel<<<grid_for(n, 256), 256, 0, s>>>(j.src_ext_id, j.old_of_new, n, j.ext_id);
-  // this GPU's share of the remaining rows: new ids hot + rank, hot + rank + world, ...
+  gather_u32_kernel<<<grid_for(j.n_flat, 256), 256, 0, s>>>(j.src_ext_id, j.old_of_new, j.n_flat, j.ext_id);
+  // this GPU's share: flat ids [own_first, own_first + own)
   if (j.own) {
-    gather_rows_kernel<<<grid_for(static_cast<uint64_t>(j.own) * 32, 256), 256, 0, s>>>(j.src_vec, j.old_of_new, j.own_first, j.world, j.own, j.row_f4, j.own_vec);
-    gather_lists_kernel<<<grid_for(static_cast<uint64_t>(j.own) * j.m0, 256), 256, 0, s>>>(j.src_l0, j.m0, j.old_of_new, j.new_of_old, j.own_first, j.world, j.own, j.own_l0);
+    gather_rows_kernel<<<grid_for(static_cast<uint64_t>(j.own) * 32, 256), 256, 0, s>>>(j.src_vec, j.old_of_new, j.own_first, j.own, j.row_f4, j.own_vec);
+    gather_lists_kernel<<<grid_for(static_cast<uint64_t>(j.own) * j.m0, 256), 256, 0, s>>>(j.src_l0, j.m0, j.old_of_new, j.new_of_old, j.own_first, j.own, j.own_l0);
   }
   return cudaGetLastError();
 }
@@ -103,7 +112,7 @@ cudaError_t partition_arrays(const PartitionJob& j, cudaStream_t s) {
 // dst[i] = src[rows[i]] (whole rows of row_f4 float4): one launch instead of one copy per row
 cudaError_t gather_rows(const float4* src, const uint32_t* d_rows, uint32_t count, uint32_t row_f4, float4* dst, cudaStream_t s) {
   if (count == 0) return cudaSuccess;
-  gather_rows_kernel<<<grid_for(static_cast<uint64_t>(count) * 32, 256), 256, 0, s>>>(src, d_rows, 0, 1, count, row_f4, dst);
+  gather_rows_kernel<<<grid_for(static_cast<uint64_t>(count) * 32, 256), 256, 0, s>>>(src, d_rows, 0, count, row_f4, dst);
   return cudaGetLastError();
 }
 

@@ -42,11 +42,11 @@ struct SearchParams {
   RoutedIo io;
 };
 
-// per warp: launch totals | resolved row addresses (partitioned handles only) | query | row/distance staging (one list) |
+// per warp: launch totals | read ids of one list (partitioned handles only, graph.h read_id) | query | row/distance staging (one list) |
 // queue distances | queue ids | visited table
 constexpr uint32_t kTotalsBytes = (kNumTotals * 8 + 15) / 16 * 16;
 __host__ __device__ inline size_t warp_smem_bytes(uint32_t q_floats, uint32_t ef_cap, uint32_t list_cap, uint32_t vis_cap, bool part) {
-  return kTotalsBytes + (part ? 8ull * list_cap + 16ull * ((list_cap + 15) / 16) : 0ull) + 4ull * (q_floats + 2 * list_cap + 2 * ef_cap + vis_cap);
+  return kTotalsBytes + (part ? 4ull * list_cap : 0ull) + 4ull * (q_floats + 2 * list_cap + 2 * ef_cap + vis_cap);
 }
 
 template <bool IP, int NCHUNK, bool PART>
@@ -60,9 +60,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, SHN_MIN_BLOCKS) search_ke
   unsigned char* base = smem_raw + warp * warp_smem_bytes(q_floats, p.ef_cap, p.list_cap, p.vis_cap, PART);
   // the launch totals live in shared memory (11 x 64 bit per warp would otherwise sit in registers for the whole kernel)
   unsigned long long* s_tot = reinterpret_cast<unsigned long long*>(base);
-  const float4** s_ptr = reinterpret_cast<const float4**>(base + kTotalsBytes);
-  uint8_t* s_ord = reinterpret_cast<uint8_t*>(base + kTotalsBytes + 8u * p.list_cap);
-  float* s_q = reinterpret_cast<float*>(base + kTotalsBytes + (PART ? 8u * p.list_cap + 16u * ((p.list_cap + 15u) / 16u) : 0u));
+  uint32_t* s_read = reinterpret_cast<uint32_t*>(base + kTotalsBytes);
+  float* s_q = reinterpret_cast<float*>(base + kTotalsBytes + (PART ? 4u * p.list_cap : 0u));
   uint32_t* s_rows = reinterpret_cast<uint32_t*>(s_q + q_floats);
   float* s_dist = reinterpret_cast<float*>(s_rows + p.list_cap);
   float* qd = s_dist + p.list_cap;
@@ -129,7 +128,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, SHN_MIN_BLOCKS) search_ke
     uint32_t c_hot = 0, c_local = 0, c_halo = 0;
     const uint32_t l0_before = c_vl0;
     beam_search<IP, NCHUNK, PART>(g, s_q, 0, p.ef, qd, qi, qsize, s_rows, s_dist, vis, c_unused, c_vl0, c_l0, c_hot, c_local, c_halo,
-                                  s_ptr, s_ord, lane);
+                                  s_read, lane);
 
     // trim to k (:296-298); the reference reports ids in heap-array order, here ascending by distance
     {

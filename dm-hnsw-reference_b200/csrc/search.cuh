@@ -123,14 +123,10 @@ __device__ __forceinline__ float tail_chain(float r, const float4& q, const floa
 #ifndef SHN_SMALL_PASSES
 #define SHN_SMALL_PASSES 1
 #endif
-// s_ptr / s_ord (PART only): the rows' addresses, already resolved by the caller (own share / peer / hot set / halo) — one
-// resolution per row, done by 32 lanes at once, instead of one per row group and pass in front of the loads — in the
-// order they are to be evaluated (rows behind NVLink first, so that they share one wave of loads); s_ord[j] = the list
-// position whose distance the j-th evaluated row is.
-template <bool IP, int NCHUNK, int PASSES = SHN_PASSES, bool PART = false>
+// On a partitioned handle s_rows holds the ids the rows are READ under (graph.h read_id: the row itself, or its halo copy).
+template <bool IP, int NCHUNK, int PASSES = SHN_PASSES>
 __device__ SHN_EVAL_ATTR void eval_rows(const DeviceGraph& g, const float* s_q, const uint32_t* s_rows, uint32_t cnt,
-                                          float* s_out, int lane, const float4* const* s_ptr = nullptr,
-                                          const uint8_t* s_ord = nullptr) {
+                                          float* s_out, int lane) {
   const int t = lane & 7, grp = lane >> 3;
   const float4* s_q4 = reinterpret_cast<const float4*>(s_q);
   // NCHUNK > 0 is the dimension itself, known at compile time: block count, odd last chunk and tail length fold to
@@ -147,8 +143,8 @@ __device__ SHN_EVAL_ATTR void eval_rows(const DeviceGraph& g, const float* s_q, 
     for (int p = 0; p < PASSES; ++p) {
       s[p] = 0.f;
       const uint32_t i = base + 4 * p + grp;
-      const uint32_t ii = i < cnt ? i : cnt - 1;  // clamp: a redundant load instead of a divergent branch
-      rp[p] = (PART ? s_ptr[ii] : vec_row<false>(g, s_rows[ii])) + t;
+      const uint32_t row = s_rows[i < cnt ? i : cnt - 1];  // clamp: a redundant load instead of a divergent branch
+      rp[p] = vec_row<false>(g, row) + t;
     }
     const uint32_t npass = min(static_cast<uint32_t>(PASSES), (cnt - base + 3) >> 2);  // warp-uniform: passes that hold at least one row
     float4 tv[PASSES];
@@ -191,7 +187,7 @@ __device__ SHN_EVAL_ATTR void eval_rows(const DeviceGraph& g, const float* s_q, 
           r = tail_chain<IP>(r, s_q4[8 * nblk + (t & 3)], tv[p], ntail, t);
         }
         const uint32_t i = base + 4 * p + grp;
-        if (t == 0 && i < cnt) s_out[PART ? s_ord[i] : i] = r;
+        if (t == 0 && i < cnt) s_out[i] = r;
       }
     }
   }
@@ -380,7 +376,7 @@ template <bool IP, int NCHUNK, bool PART = false>
 __device__ __forceinline__ void beam_search(const DeviceGraph& g, const float* s_q, uint32_t level, uint32_t ef, float* qd,
                                             uint32_t* qi, uint32_t& qsize, uint32_t* s_rows, float* s_dist, VisitedSet& vis,
                                             uint32_t& c_dist, uint32_t& c_vis, uint32_t& c_lists, uint32_t& c_hot,
-                                            uint32_t& c_local, uint32_t& c_halo, const float4** s_ptr, uint8_t* s_ord, int lane) {
+                                            uint32_t& c_local, uint32_t& c_halo, uint32_t* s_read, int lane) {
   const uint32_t width = level == 0 ? g.m0 : g.m;
   uint32_t lb = 0;  // every entry below lb is expanded
   for (;;) {
@@ -424,43 +420,23 @@ __device__ __forceinline__ void beam_search(const DeviceGraph& g, const float* s
     if (cnt == 0) continue;
     c_vis += cnt; c_dist += cnt;
     if (PART) {
-      // where the rows of this expansion live (and, during a warm-up pass, how often each is read); the rows behind NVLink
-      // are evaluated first, together: a wave of loads takes as long as its slowest row
-      uint32_t loc[2], idx[2], rem[2], oth[2];
-      const uint32_t below = (1u << lane) - 1u;
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        const uint32_t i = 32u * c + lane;
+      // the ids the rows are read under (a halo copy replaces a row of a peer's share), where they live, and — during a
+      // warm-up pass — how often each is read
+      for (uint32_t i = lane; i < ((cnt + 31u) & ~31u); i += 32) {
         const bool in = i < cnt;
-        loc[c] = kLocHot; idx[c] = 0;
+        uint32_t cls = kRowPeer + 1;
         if (in) {
           const uint32_t row = s_rows[i];
           if (g.visit_count) atomicAdd(g.visit_count + row, 1u);
-          resolve_row(g, row, loc[c], idx[c]);
+          s_read[i] = read_id<true>(g, row, cls);
         }
-        const bool remote = in && loc[c] < 8u && loc[c] != g.rank;
-        rem[c] = __ballot_sync(kFull, remote);
-        oth[c] = __ballot_sync(kFull, in && !remote);
-        c_hot += __popc(__ballot_sync(kFull, in && loc[c] == kLocHot));
-        c_local += __popc(__ballot_sync(kFull, in && loc[c] == g.rank));
-        c_halo += __popc(__ballot_sync(kFull, in && loc[c] == kLocHalo));
-        if (cnt <= 32) break;  // warp-uniform
-      }
-      const uint32_t nrem0 = __popc(rem[0]), nrem = nrem0 + (cnt > 32 ? __popc(rem[1]) : 0u), noth0 = __popc(oth[0]);
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        const uint32_t i = 32u * c + lane;
-        if (i < cnt) {
-          const bool remote = (rem[c] >> lane) & 1u;
-          const uint32_t pos = remote ? (c ? nrem0 : 0u) + __popc(rem[c] & below) : nrem + (c ? noth0 : 0u) + __popc(oth[c] & below);
-          s_ptr[pos] = vec_at(g, loc[c], idx[c]);
-          s_ord[pos] = static_cast<uint8_t>(i);
-        }
-        if (cnt <= 32) break;
+        c_hot += __popc(__ballot_sync(kFull, cls == kRowHot));
+        c_local += __popc(__ballot_sync(kFull, cls == kRowOwn));
+        c_halo += __popc(__ballot_sync(kFull, cls == kRowHalo));
       }
       __syncwarp();
     }
-    eval_rows<IP, NCHUNK, SHN_PASSES, PART>(g, s_q, s_rows, cnt, s_dist, lane, s_ptr, s_ord);
+    eval_rows<IP, NCHUNK, SHN_PASSES>(g, s_q, PART ? s_read : s_rows, cnt, s_dist, lane);
 
     // admission against the running farthest distance (:456-465, heap.hh:34-41), all neighbours in one merge
     const uint32_t at = queue_merge(qd, qi, qsize, ef, s_rows, s_dist, cnt, lane);

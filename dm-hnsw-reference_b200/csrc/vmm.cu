@@ -1,7 +1,6 @@
 #include "vmm.h"
 
 #include <cstdint>
-#include <cstdlib>
 
 namespace shn {
 namespace {
@@ -91,14 +90,6 @@ cudaError_t map_block(const Driver& d, VmmBlock& b, int device, const char** why
 }  // namespace
 
 cudaError_t vmm_alloc(VmmBlock& b, size_t bytes, int device, const char** why) {
-  if (const char* plain = getenv("SHN_SHARE_PLAIN"); plain && plain[0] == '1') {
-    // diagnostic only (tools/part_overhead.py): a cudaMalloc share, usable by handles of the same process, not exportable
-    b = VmmBlock{};
-    b.size = bytes; b.plain = true;
-    const cudaError_t e = cudaMalloc(&b.ptr, bytes);
-    if (e != cudaSuccess) { *why = "cudaMalloc"; b = VmmBlock{}; }
-    return e;
-  }
   const Driver& d = driver();
   if (!d.ok) { *why = "CUDA driver lacks the virtual memory management API"; return cudaErrorNotSupported; }
   cudaFree(nullptr);  // make sure the primary context exists
@@ -119,7 +110,7 @@ cudaError_t vmm_alloc(VmmBlock& b, size_t bytes, int device, const char** why) {
 
 cudaError_t vmm_export_fd(const VmmBlock& b, int* fd, const char** why) {
   const Driver& d = driver();
-  if (!d.ok || !b.ptr || b.plain) { *why = "nothing to export"; return cudaErrorInvalidValue; }
+  if (!d.ok || !b.handle) { *why = "nothing to export"; return cudaErrorInvalidValue; }
   int out = -1;
   if (d.MemExportToShareableHandle(&out, b.handle, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0) != CUDA_SUCCESS) {
     *why = "cuMemExportToShareableHandle"; return cudaErrorUnknown;
@@ -145,9 +136,93 @@ cudaError_t vmm_import_fd(VmmBlock& b, int fd, size_t size, int device, const ch
   return e;
 }
 
+cudaError_t vmm_granularity(int device, size_t* gran, const char** why) {
+  const Driver& d = driver();
+  if (!d.ok) { *why = "CUDA driver lacks the virtual memory management API"; return cudaErrorNotSupported; }
+  cudaFree(nullptr);
+  const CUmemAllocationProp p = prop_for(device);
+  if (d.MemGetAllocationGranularity(gran, &p, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED) != CUDA_SUCCESS || *gran == 0) {
+    *why = "cuMemGetAllocationGranularity"; return cudaErrorUnknown;
+  }
+  return cudaSuccess;
+}
+
+cudaError_t vmm_reserve(VmmSpace& s, size_t bytes, size_t align, const char** why) {
+  const Driver& d = driver();
+  if (!d.ok) { *why = "CUDA driver lacks the virtual memory management API"; return cudaErrorNotSupported; }
+  cudaFree(nullptr);
+  CUdeviceptr va = 0;
+  if (d.MemAddressReserve(&va, bytes, align, 0, 0) != CUDA_SUCCESS) { *why = "cuMemAddressReserve"; return cudaErrorMemoryAllocation; }
+  s.base = reinterpret_cast<void*>(va);
+  s.size = bytes;
+  return cudaSuccess;
+}
+
+void vmm_release(VmmSpace& s) {
+  const Driver& d = driver();
+  if (d.ok && s.base) d.MemAddressFree(reinterpret_cast<CUdeviceptr>(s.base), s.size);
+  s = VmmSpace{};
+}
+
+cudaError_t vmm_create(VmmBlock& b, size_t bytes, int device, const char** why) {
+  const Driver& d = driver();
+  size_t gran = 0;
+  cudaError_t e = vmm_granularity(device, &gran, why);
+  if (e != cudaSuccess) return e;
+  const CUmemAllocationProp p = prop_for(device);
+  b = VmmBlock{};
+  b.size = (bytes + gran - 1) / gran * gran;
+  CUmemGenericAllocationHandle h = 0;
+  if (d.MemCreate(&h, b.size, &p, 0) != CUDA_SUCCESS) { *why = "cuMemCreate"; b = VmmBlock{}; return cudaErrorMemoryAllocation; }
+  b.handle = h;
+  return cudaSuccess;
+}
+
+cudaError_t vmm_import_handle(VmmBlock& b, int fd, size_t size, const char** why) {
+  const Driver& d = driver();
+  if (!d.ok) { *why = "CUDA driver lacks the virtual memory management API"; return cudaErrorNotSupported; }
+  cudaFree(nullptr);
+  b = VmmBlock{};
+  b.size = size;
+  b.imported = true;
+  CUmemGenericAllocationHandle h = 0;
+  if (d.MemImportFromShareableHandle(&h, reinterpret_cast<void*>(static_cast<uintptr_t>(fd)), CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR) != CUDA_SUCCESS) {
+    *why = "cuMemImportFromShareableHandle"; b = VmmBlock{}; return cudaErrorUnknown;
+  }
+  b.handle = h;
+  return cudaSuccess;
+}
+
+cudaError_t vmm_place(const VmmSpace& s, size_t offset, size_t size, unsigned long long handle, int device, const char** why) {
+  const Driver& d = driver();
+  if (!d.ok || !s.base || offset + size > s.size) { *why = "bad placement"; return cudaErrorInvalidValue; }
+  const CUdeviceptr va = reinterpret_cast<CUdeviceptr>(s.base) + offset;
+  if (d.MemMap(va, size, 0, handle, 0) != CUDA_SUCCESS) { *why = "cuMemMap"; return cudaErrorMemoryAllocation; }
+  CUmemAccessDesc acc = {};
+  acc.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+  acc.location.id = device;
+  acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+  if (d.MemSetAccess(va, size, &acc, 1) != CUDA_SUCCESS) {
+    d.MemUnmap(va, size);
+    *why = "cuMemSetAccess (no peer access between the two GPUs?)";
+    return cudaErrorPeerAccessUnsupported;
+  }
+  return cudaSuccess;
+}
+
+void vmm_unplace(const VmmSpace& s, size_t offset, size_t size) {
+  const Driver& d = driver();
+  if (d.ok && s.base) d.MemUnmap(reinterpret_cast<CUdeviceptr>(s.base) + offset, size);
+}
+
+void vmm_drop(VmmBlock& b) {
+  const Driver& d = driver();
+  if (d.ok && b.handle) d.MemRelease(b.handle);
+  b = VmmBlock{};
+}
+
 void vmm_free(VmmBlock& b) {
   const Driver& d = driver();
-  if (b.plain) { cudaFree(b.ptr); b = VmmBlock{}; return; }
   if (!d.ok || !b.ptr) { b = VmmBlock{}; return; }
   const CUdeviceptr va = reinterpret_cast<CUdeviceptr>(b.ptr);
   d.MemUnmap(va, b.size);

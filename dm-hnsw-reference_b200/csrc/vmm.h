@@ -17,7 +17,6 @@ struct VmmBlock {
   size_t size = 0;          // padded to the allocation granularity
   unsigned long long handle = 0;  // CUmemGenericAllocationHandle
   bool imported = false;
-  bool plain = false;       // SHN_SHARE_PLAIN=1 diagnostic: cudaMalloc instead of cuMemCreate
 };
 
 // Allocate `bytes` of device memory on `device`, read/write mapped for that device, exportable as a POSIX fd.
@@ -27,5 +26,27 @@ cudaError_t vmm_export_fd(const VmmBlock& b, int* fd, const char** why);
 // Map a block exported by another process (or this one) into this process for `device`.
 cudaError_t vmm_import_fd(VmmBlock& b, int fd, size_t size, int device, const char** why);
 void vmm_free(VmmBlock& b);
+
+// One flat address range per array of a partitioned index (graph.h "flat numbering"): the replicated hot set, this GPU's
+// share, every peer's share and the halo are separate physical allocations mapped side by side into ONE reservation, so
+// that a row is at base + row * stride wherever it lives and the MMU does what a lookup table would otherwise do.
+struct VmmSpace {
+  void* base = nullptr;
+  size_t size = 0;
+};
+// physical allocation granularity on `device` (pieces of a space start at multiples of it)
+cudaError_t vmm_granularity(int device, size_t* gran, const char** why);
+cudaError_t vmm_reserve(VmmSpace& s, size_t bytes, size_t align, const char** why);
+void vmm_release(VmmSpace& s);
+// A physical allocation that is not mapped anywhere yet (exportable; b.ptr stays null until it is placed).
+cudaError_t vmm_create(VmmBlock& b, size_t bytes, int device, const char** why);
+// Import without mapping.
+cudaError_t vmm_import_handle(VmmBlock& b, int fd, size_t size, const char** why);
+// Map allocation `handle` (size bytes) at s.base + offset, read/write for `device` (and, unless peer_access is false, every GPU of this
+// process that can reach it).  The same allocation may be placed into several spaces.
+cudaError_t vmm_place(const VmmSpace& s, size_t offset, size_t size, unsigned long long handle, int device, const char** why);
+void vmm_unplace(const VmmSpace& s, size_t offset, size_t size);
+// Drop the allocation handle (mappings made from it stay valid until unmapped).
+void vmm_drop(VmmBlock& b);
 
 }  // namespace shn

@@ -124,8 +124,10 @@ int shn_set_option(shn_index*, const char* key, int64_t value);
  * the node (src/cache/cache.hh, admission src/hnsw/hnsw.hh:447-448).  Here: one process per GPU; each builds or loads the
  * full index, (optionally) runs warm-up queries with visit counting, all-reduces the counts, and keeps
  *   - the hot set (all nodes with level > 0 + the most visited level-0 nodes, cache_ratio_pct % of the nodes) replicated,
- *   - 1/world of the remaining rows (round-robin);
- * the other shares are read over NVLink through peer-mapped pointers.  Results do not depend on the partitioning. */
+ *   - its share of the remaining rows (round-robin, or the rows shn_placement_fit gave it);
+ * the other shares are its peers' physical memory mapped into the same address range (CUDA virtual memory management):
+ * a row is read at base + row * stride wherever it lives, over NVLink if it is a peer's.  Results do not depend on the
+ * partitioning. */
 int shn_index_count_visits(shn_index*, int enable);   /* on: allocate + zero the per-node counters; searches then count */
 /* copy the counters to (write_back = 0) or from (write_back = 1) a device buffer of n u32 — the caller all-reduces.
  * Complete on return; with write_back the caller's writes to d_counts must have completed (the call waits for no stream
@@ -157,12 +159,13 @@ int shn_index_partition_build_halo(shn_index*, uint32_t ratio_pct, uint64_t* hal
  * shares with their own numbering); any output may be NULL. */
 int shn_index_partition_info(const shn_index*, uint32_t* hot, uint32_t* own, uint32_t* entry_row);
 /* This GPU's share as two POSIX file descriptors (vectors, level-0 lists; CUDA virtual-memory-management export — the
- * caller passes them to the other processes over a Unix socket and closes them), their mapped sizes, and the raw device
- * pointers (for peers inside the same process).  Any of the three outputs may be NULL. */
-int shn_index_partition_export(const shn_index*, int* fds /*2*/, uint64_t* sizes /*2*/, uint64_t* raw_ptrs /*2*/);
-/* Attach rank `peer`'s share: fds + sizes received from another process, or raw_ptrs of a handle in this process.
- * Searching needs every peer attached. */
-int shn_index_partition_attach(shn_index*, int peer, const int* fds, const uint64_t* sizes, const uint64_t* raw_ptrs);
+ * caller passes them to the other processes over a Unix socket and closes them), their mapped sizes, and — for peers
+ * inside the same process — two opaque tokens (valid while this handle lives).  Any of the three outputs may be NULL. */
+int shn_index_partition_export(const shn_index*, int* fds /*2*/, uint64_t* sizes /*2*/, uint64_t* tokens /*2*/);
+/* Attach rank `peer`'s share: fds + sizes received from another process, or the tokens of a handle in this process.  The
+ * share is mapped into this handle's own address ranges at the place the flat numbering gives it, so that a row of a
+ * peer is read like any other row (over NVLink).  Searching needs every peer attached. */
+int shn_index_partition_attach(shn_index*, int peer, const int* fds, const uint64_t* sizes, const uint64_t* tokens);
 
 /* ---- query routing between the GPUs of a partitioned index, fused with the exchange (csrc/router.cu) ---------------
  * The reference: QueryRouter (src/router/query_router.hh:280-387) sends a query to the compute node of its nearest

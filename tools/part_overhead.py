@@ -1,7 +1,6 @@
 """Scratch (ONE GPU): what the partitioned kernel variant costs when nothing is remote.  The ranks of a 2-way partition are
 emulated on one device (raw-pointer attach), so every "remote" read is a local HBM read: the difference to the full index is
-the kernel's own overhead (row resolution, statistics) plus whatever the share's memory mapping costs (SHN_SHARE_PLAIN=1:
-cudaMalloc shares instead of cuMemCreate ones)."""
+the partitioned kernel variant's own overhead (read ids, statistics)."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")]
@@ -35,7 +34,7 @@ for mode in ("cluster", "round-robin"):
     t_part = best(parts[0], ids)
     st = parts[0].search_device(q.data_ptr(), nq, 10, ef, ids.data_ptr())
     tot = st["rows_hot"] + st["rows_local"] + st["rows_remote"] + st["rows_halo"]
-    print(f"plain={os.environ.get('SHN_SHARE_PLAIN', '0')} {mode}: full {t_full:.1f} ms, partition (all local HBM) {t_part:.1f} ms (+{100 * (t_part / t_full - 1):.1f}%), "
+    print(f"{mode}: full {t_full:.1f} ms, partition (all local HBM) {t_part:.1f} ms (+{100 * (t_part / t_full - 1):.1f}%), "
           f"identical {(ids == ref).all(1).float().mean().item():.4f}, hot {st['rows_hot'] / tot:.3f} own {st['rows_local'] / tot:.3f} other {st['rows_remote'] / tot:.3f}", flush=True)
     for p in parts:
         p.close()
