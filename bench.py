@@ -356,6 +356,8 @@ def partitioned_block(pkg, args, dist, rank, world, dev, local_rank, peak):
     total_ms = ev[0].elapsed_time(ev[1])
     clk = clocks.stop()
     # one more step with the phases timed and the counters read (outside the timed region)
+    dist.barrier(); torch.cuda.synchronize()
+    fence()
     ev[0].record()
     router.scatter(batches[0].data_ptr(), nq, stream=stream)
     fence()
@@ -390,7 +392,9 @@ def partitioned_block(pkg, args, dist, rank, world, dev, local_rank, peak):
     rows = float(frac[0] + frac[1] + frac[2] + frac[4])
     return dict(workload=wl["label"], ef=ef, k=K, recall_at_10=round(rec, 4), recall_whole_index=whole["recall"],
                 identical_to_whole_index=dict(partition_unrouted=round(float(ident[0]), 6), routed=round(float(ident[1]), 6),
-                                              note="fraction of the step's queries whose id list equals the whole-index answer, min over ranks"),
+                                              note="fraction of the step's queries whose id list equals the whole-index answer, min over ranks (the partitioned kernel "
+                                                   "evaluates the NVLink rows of a list first: two candidates of one list at the exact same "
+                                                   "distance can swap)"),
                 processed_all_ranks=int(frac[3]), value=round(qps, 1), unit="queries/s",
                 steps=steps, ms_per_step=round(total_ms / steps, 3), queries_per_step_per_gpu=nq,
                 design="graph partitioned by k-means cluster over the GPUs' HBM + replicated hot set + per-GPU halo (local copies of the "
@@ -433,7 +437,7 @@ def main():
     ap.add_argument("--part-steps", type=int, default=5)
     ap.add_argument("--part-recall-queries", type=int, default=5_000)
     ap.add_argument("--cache-ratio", type=int, default=8, help="partitioned: replicated hot set in %% of the nodes (--cache-ratio of the reference)")
-    ap.add_argument("--halo-ratio", type=int, default=8,
+    ap.add_argument("--halo-ratio", type=int, default=16,
                     help="partitioned: every GPU also caches this %% of the nodes from its peers' shares — the rows its own routed "
                          "queries read most (shn_index_partition_build_halo); 0 = off")
     ap.add_argument("--route-slack", type=float, default=0.25, help="a GPU takes at most (1 + slack) / N of a batch (query_router.hh:106-151)")

@@ -379,6 +379,10 @@ __device__ __forceinline__ void beam_search(const DeviceGraph& g, const float* s
                                             uint32_t& c_local, uint32_t& c_halo, uint32_t* s_read, int lane) {
   const uint32_t width = level == 0 ? g.m0 : g.m;
   uint32_t lb = 0;  // every entry below lb is expanded
+#ifndef SHN_NO_LIST_AHEAD
+  // the list of the entry that will be expanded next, requested before the merge of the current expansion (see below)
+  uint32_t ahead_row = kInvalid, ahead_nb0 = kInvalid, ahead_nb1 = kInvalid;
+#endif
   for (;;) {
     // next_candidates.pop(): the closest entry not yet expanded
     uint32_t pos = kInvalid;
@@ -396,11 +400,18 @@ __device__ __forceinline__ void beam_search(const DeviceGraph& g, const float* s
     ++c_lists;
 
     // read_neighborlist (:437)
-    const uint32_t* list = level == 0 ? l0_row<PART>(g, cand)
-                                      : g.up + (static_cast<size_t>(__ldg(g.up_base + cand)) + (level - 1)) * g.m;
-    const uint32_t nb0 = static_cast<uint32_t>(lane) < width ? __ldg(list + lane) : kInvalid;
-    uint32_t nb1 = kInvalid;
-    if (width > 32) nb1 = static_cast<uint32_t>(lane) + 32 < width ? __ldg(list + lane + 32) : kInvalid;
+    uint32_t nb0 = kInvalid, nb1 = kInvalid;
+#ifndef SHN_NO_LIST_AHEAD
+    if (cand == ahead_row) {  // warp-uniform: already on its way
+      nb0 = ahead_nb0; nb1 = ahead_nb1;
+    } else
+#endif
+    {
+      const uint32_t* list = level == 0 ? l0_row<PART>(g, cand)
+                                        : g.up + (static_cast<size_t>(__ldg(g.up_base + cand)) + (level - 1)) * g.m;
+      if (static_cast<uint32_t>(lane) < width) nb0 = __ldg(list + lane);
+      if (width > 32 && static_cast<uint32_t>(lane) + 32 < width) nb1 = __ldg(list + lane + 32);
+    }
 
     // the visited filter, in stored order (:440-443)
     uint32_t cnt = 0;
@@ -422,22 +433,77 @@ __device__ __forceinline__ void beam_search(const DeviceGraph& g, const float* s
     if (PART) {
       // the ids the rows are read under (a halo copy replaces a row of a peer's share), where they live, and — during a
       // warm-up pass — how often each is read
-      for (uint32_t i = lane; i < ((cnt + 31u) & ~31u); i += 32) {
+      for (uint32_t base = 0; base < cnt; base += 32) {
+        const uint32_t i = base + lane;
         const bool in = i < cnt;
-        uint32_t cls = kRowPeer + 1;
+        uint32_t cls = kRowPeer + 1, row = 0, rd = 0;
         if (in) {
-          const uint32_t row = s_rows[i];
+          row = s_rows[i];
           if (g.visit_count) atomicAdd(g.visit_count + row, 1u);
-          s_read[i] = read_id<true>(g, row, cls);
+          rd = read_id<true>(g, row, cls);
         }
         c_hot += __popc(__ballot_sync(kFull, cls == kRowHot));
         c_local += __popc(__ballot_sync(kFull, cls == kRowOwn));
         c_halo += __popc(__ballot_sync(kFull, cls == kRowHalo));
+        // Rows behind NVLink go to the front of the list (both groups keep their stored order): a wave of loads takes as long
+        // as its slowest row, so the remote rows should share one wave.  What reaches queue_merge is a permutation of the
+        // same candidates; only the order of two candidates of this list at the exact same distance can differ.
+        const uint32_t in_mask = __ballot_sync(kFull, in);
+        const uint32_t rem_mask = __ballot_sync(kFull, cls == kRowPeer);
+        uint32_t pos = i;
+        if (rem_mask != 0u && rem_mask != in_mask) {  // warp-uniform
+          const uint32_t below = (1u << lane) - 1u;
+          pos = base + ((rem_mask >> lane) & 1u ? __popc(rem_mask & below) : __popc(rem_mask) + __popc(in_mask & ~rem_mask & below));
+          __syncwarp();
+          if (in) s_rows[pos] = row;
+        }
+        if (in) s_read[pos] = rd;
       }
       __syncwarp();
     }
     eval_rows<IP, NCHUNK, SHN_PASSES>(g, s_q, PART ? s_read : s_rows, cnt, s_dist, lane);
 
+#ifndef SHN_NO_LIST_AHEAD
+    // Which entry is expanded next is known before the merge: the closer of the first unexpanded entry of the queue as it
+    // stands and the closest candidate of this list (old entries first on equal distance, list order among the candidates).
+    // Its list is requested now, so that the load is in flight while the merge runs — one memory round trip per
+    // expansion leaves the critical path.  A wrong guess is impossible by construction, but the use above still checks the row.
+    {
+      const float kInf = __int_as_float(0x7f800000);
+      uint32_t op = kInvalid;
+      for (uint32_t b = lb & ~31u; b < qsize; b += 32) {
+        const uint32_t j = b + lane;
+        const bool un = j < qsize && j >= lb && !(qi[j] & kExpanded);
+        const uint32_t mask = __ballot_sync(kFull, un);
+        if (mask) { op = b + __ffs(mask) - 1; break; }
+      }
+      const float od = op != kInvalid ? qd[op] : kInf;
+      float nd = static_cast<uint32_t>(lane) < cnt ? s_dist[lane] : kInf;
+      uint32_t ni = lane;
+      if (cnt > 32 && static_cast<uint32_t>(lane) + 32 < cnt) {
+        const float d1 = s_dist[lane + 32];
+        if (d1 < nd) { nd = d1; ni = lane + 32; }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float xd = __shfl_xor_sync(kFull, nd, o);
+        const uint32_t xi = __shfl_xor_sync(kFull, ni, o);
+        if (xd < nd || (xd == nd && xi < ni)) { nd = xd; ni = xi; }
+      }
+      const bool take_new = nd < od;
+      const float next_d = take_new ? nd : od;
+      const uint32_t next_row = take_new ? s_rows[ni] : (op != kInvalid ? qi[op] : kInvalid);
+      ahead_row = kInvalid;
+      if (next_row != kInvalid && !(qsize == ef && next_d >= qd[ef - 1])) {
+        ahead_row = next_row;
+        const uint32_t* list = level == 0 ? l0_row<PART>(g, next_row)
+                                          : g.up + (static_cast<size_t>(__ldg(g.up_base + next_row)) + (level - 1)) * g.m;
+        ahead_nb0 = kInvalid; ahead_nb1 = kInvalid;
+        if (static_cast<uint32_t>(lane) < width) ahead_nb0 = __ldg(list + lane);
+        if (width > 32 && static_cast<uint32_t>(lane) + 32 < width) ahead_nb1 = __ldg(list + lane + 32);
+      }
+    }
+#endif
     // admission against the running farthest distance (:456-465, heap.hh:34-41), all neighbours in one merge
     const uint32_t at = queue_merge(qd, qi, qsize, ef, s_rows, s_dist, cnt, lane);
     if (at < lb) lb = at;
