@@ -32,9 +32,11 @@ inline uint64_t ref_alloc_bytes(uint32_t dim, uint32_t m, uint32_t level) {
 
 // Stored order of a row's components ("AVX-lane-major blocks", see search.cuh): the 16*(dim/16) leading elements are
 // grouped in blocks of 32 floats = two 16-element chunks of the reference's distance loop (distance.hh:88-110); inside
-// a block the 16-byte piece t (0..7) holds {v[t], v[8+t], v[16+t], v[24+t]} — everything AVX lane t needs from the two
-// chunks.  An odd last chunk fills half of its block (the rest is zero).  The dim%16 tail elements follow in natural
-// order.  The row stride is rounded up to whole 128-byte lines.
+// a block the 16-byte piece t (0..7) holds {v[t], v[16+t], v[8+t], v[24+t]} — everything AVX lane t needs from the two
+// chunks, arranged as two aligned pairs (first halves of chunk c and c+1 | second halves of chunk c and c+1) so that the
+// two chunks go through the packed fp32x2 pipe together (search.cuh block_accumulate).  An odd last chunk fills half
+// of its block (the rest is zero).  The dim%16 tail elements follow in natural order.  The row stride is rounded up to
+// whole 128-byte lines.
 #ifdef __CUDACC__
 #define SHN_HD __host__ __device__
 #else
@@ -45,8 +47,13 @@ SHN_HD inline uint32_t row_stride_f4(uint32_t dim) { return ((32u * row_blocks(d
 SHN_HD inline uint32_t row_pos(uint32_t dim, uint32_t e) {
   const uint32_t d16 = dim & ~15u;
   if (e >= d16) return 32u * row_blocks(dim) + (e - d16);
-  const uint32_t w = e & 31u;
-  return (e & ~31u) + 4u * (w & 7u) + (w >> 3);
+  const uint32_t w = e & 31u, q = w >> 3;  // q: quarter of the block; quarters 1 and 2 swap places inside a piece
+  return (e & ~31u) + 4u * (w & 7u) + (((q & 1u) << 1) | (q >> 1));
+}
+// inverse of row_pos inside the blocks: stored position -> element
+SHN_HD inline uint32_t row_elem(uint32_t pos) {
+  const uint32_t w = pos & 31u, s = w & 3u;
+  return (pos & ~31u) + 8u * (((s & 1u) << 1) | (s >> 1)) + (w >> 2);
 }
 
 struct HostGraph {

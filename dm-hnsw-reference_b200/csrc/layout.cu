@@ -16,8 +16,7 @@ __global__ void to_layout_kernel(const float* __restrict__ src, float* __restric
     const uint32_t d16 = dim & ~15u, nblk = row_blocks(dim);
     float v = 0.f;
     if (pos < 32u * nblk) {
-      const uint32_t w = pos & 31u;
-      const uint32_t e = (pos & ~31u) + 8u * (w & 3u) + (w >> 2);
+      const uint32_t e = row_elem(pos);
       if (e < d16) v = src[row * dim + e];
     } else if (pos - 32u * nblk < (dim & 15u)) {
       v = src[row * dim + d16 + (pos - 32u * nblk)];

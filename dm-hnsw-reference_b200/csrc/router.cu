@@ -172,8 +172,7 @@ __global__ void route_scatter_kernel(const float* __restrict__ queries, uint32_t
       const uint32_t pos = 4 * f + e4;
       float x = 0.f;
       if (pos < 32u * nblk) {  // inverse of row_pos (layout.cu)
-        const uint32_t w = pos & 31u;
-        const uint32_t e = (pos & ~31u) + 8u * (w & 3u) + (w >> 2);
+        const uint32_t e = row_elem(pos);
         if (e < d16) x = __ldg(src + e);
       } else if (pos - 32u * nblk < ntail) {
         x = __ldg(src + d16 + (pos - 32u * nblk));

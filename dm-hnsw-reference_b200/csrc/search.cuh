@@ -50,19 +50,37 @@ __device__ __forceinline__ float4 ldg_f4(const float4* p) { return __ldg(p); }
 // measured better than 16 rows in flight at 128 registers and 4 CTAs/SM).
 // ---------------------------------------------------------------------------------------------------------------
 
+// One 16-byte piece q / a = {first half of chunk c, first half of chunk c+1, second half of chunk c, second half of
+// chunk c+1} for AVX lane t.  The two chunks go through the packed fp32x2 pipe together (sub.f32x2 / mul.f32x2 / fma.f32x2,
+// sm_100: each half is an ordinary IEEE fp32 operation, so the bits are those of the scalar sequence) and are then
+// added to the running sum one after the other, as the reference does.
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
 template <bool IP>
 __device__ __forceinline__ void block_accumulate(const float4& q, const float4& a, float& s, bool second_chunk) {
+  const unsigned long long q0 = pack2(q.x, q.y), q1 = pack2(q.z, q.w), a0 = pack2(a.x, a.y), a1 = pack2(a.z, a.w);
+  unsigned long long f;
   if (IP) {
-    s = __fadd_rn(s, __fmaf_rn(q.x, a.x, __fmul_rn(q.y, a.y)));
-    if (second_chunk) s = __fadd_rn(s, __fmaf_rn(q.z, a.z, __fmul_rn(q.w, a.w)));
+    unsigned long long m;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(m) : "l"(q1), "l"(a1));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(f) : "l"(q0), "l"(a0), "l"(m));
   } else {
-    float d0 = __fsub_rn(q.x, a.x), d1 = __fsub_rn(q.y, a.y);
-    s = __fadd_rn(s, __fmaf_rn(d0, d0, __fmul_rn(d1, d1)));
-    if (second_chunk) {
-      d0 = __fsub_rn(q.z, a.z); d1 = __fsub_rn(q.w, a.w);
-      s = __fadd_rn(s, __fmaf_rn(d0, d0, __fmul_rn(d1, d1)));
-    }
+    unsigned long long d0, d1, m;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d0) : "l"(q0), "l"(a0));
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d1) : "l"(q1), "l"(a1));
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(m) : "l"(d1), "l"(d1));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(f) : "l"(d0), "l"(d0), "l"(m));
   }
+  float f_lo, f_hi;
+  unpack2(f, f_lo, f_hi);
+  s = __fadd_rn(s, f_lo);
+  if (second_chunk) s = __fadd_rn(s, f_hi);
 }
 
 // Horizontal step (distance.hh:40 / :134-139); the result is valid in lane t == 0 of the row group.
@@ -379,10 +397,6 @@ __device__ __forceinline__ void beam_search(const DeviceGraph& g, const float* s
                                             uint32_t& c_local, uint32_t& c_halo, uint32_t* s_read, int lane) {
   const uint32_t width = level == 0 ? g.m0 : g.m;
   uint32_t lb = 0;  // every entry below lb is expanded
-#ifndef SHN_NO_LIST_AHEAD
-  // the list of the entry that will be expanded next, requested before the merge of the current expansion (see below)
-  uint32_t ahead_row = kInvalid, ahead_nb0 = kInvalid, ahead_nb1 = kInvalid;
-#endif
   for (;;) {
     // next_candidates.pop(): the closest entry not yet expanded
     uint32_t pos = kInvalid;
@@ -400,18 +414,11 @@ __device__ __forceinline__ void beam_search(const DeviceGraph& g, const float* s
     ++c_lists;
 
     // read_neighborlist (:437)
-    uint32_t nb0 = kInvalid, nb1 = kInvalid;
-#ifndef SHN_NO_LIST_AHEAD
-    if (cand == ahead_row) {  // warp-uniform: already on its way
-      nb0 = ahead_nb0; nb1 = ahead_nb1;
-    } else
-#endif
-    {
-      const uint32_t* list = level == 0 ? l0_row<PART>(g, cand)
-                                        : g.up + (static_cast<size_t>(__ldg(g.up_base + cand)) + (level - 1)) * g.m;
-      if (static_cast<uint32_t>(lane) < width) nb0 = __ldg(list + lane);
-      if (width > 32 && static_cast<uint32_t>(lane) + 32 < width) nb1 = __ldg(list + lane + 32);
-    }
+    const uint32_t* list = level == 0 ? l0_row<PART>(g, cand)
+                                      : g.up + (static_cast<size_t>(__ldg(g.up_base + cand)) + (level - 1)) * g.m;
+    const uint32_t nb0 = static_cast<uint32_t>(lane) < width ? __ldg(list + lane) : kInvalid;
+    uint32_t nb1 = kInvalid;
+    if (width > 32) nb1 = static_cast<uint32_t>(lane) + 32 < width ? __ldg(list + lane + 32) : kInvalid;
 
     // the visited filter, in stored order (:440-443)
     uint32_t cnt = 0;
@@ -463,47 +470,10 @@ __device__ __forceinline__ void beam_search(const DeviceGraph& g, const float* s
     }
     eval_rows<IP, NCHUNK, SHN_PASSES>(g, s_q, PART ? s_read : s_rows, cnt, s_dist, lane);
 
-#ifndef SHN_NO_LIST_AHEAD
-    // Which entry is expanded next is known before the merge: the closer of the first unexpanded entry of the queue as it
-    // stands and the closest candidate of this list (old entries first on equal distance, list order among the candidates).
-    // Its list is requested now, so that the load is in flight while the merge runs — one memory round trip per
-    // expansion leaves the critical path.  A wrong guess is impossible by construction, but the use above still checks the row.
-    {
-      const float kInf = __int_as_float(0x7f800000);
-      uint32_t op = kInvalid;
-      for (uint32_t b = lb & ~31u; b < qsize; b += 32) {
-        const uint32_t j = b + lane;
-        const bool un = j < qsize && j >= lb && !(qi[j] & kExpanded);
-        const uint32_t mask = __ballot_sync(kFull, un);
-        if (mask) { op = b + __ffs(mask) - 1; break; }
-      }
-      const float od = op != kInvalid ? qd[op] : kInf;
-      float nd = static_cast<uint32_t>(lane) < cnt ? s_dist[lane] : kInf;
-      uint32_t ni = lane;
-      if (cnt > 32 && static_cast<uint32_t>(lane) + 32 < cnt) {
-        const float d1 = s_dist[lane + 32];
-        if (d1 < nd) { nd = d1; ni = lane + 32; }
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const float xd = __shfl_xor_sync(kFull, nd, o);
-        const uint32_t xi = __shfl_xor_sync(kFull, ni, o);
-        if (xd < nd || (xd == nd && xi < ni)) { nd = xd; ni = xi; }
-      }
-      const bool take_new = nd < od;
-      const float next_d = take_new ? nd : od;
-      const uint32_t next_row = take_new ? s_rows[ni] : (op != kInvalid ? qi[op] : kInvalid);
-      ahead_row = kInvalid;
-      if (next_row != kInvalid && !(qsize == ef && next_d >= qd[ef - 1])) {
-        ahead_row = next_row;
-        const uint32_t* list = level == 0 ? l0_row<PART>(g, next_row)
-                                          : g.up + (static_cast<size_t>(__ldg(g.up_base + next_row)) + (level - 1)) * g.m;
-        ahead_nb0 = kInvalid; ahead_nb1 = kInvalid;
-        if (static_cast<uint32_t>(lane) < width) ahead_nb0 = __ldg(list + lane);
-        if (width > 32 && static_cast<uint32_t>(lane) + 32 < width) ahead_nb1 = __ldg(list + lane + 32);
-      }
-    }
-#endif
+    // (Requesting the NEXT expansion's list here, before the merge — the entry is known exactly: the closer of the first
+    // unexpanded queue entry and the closest candidate of this list — was measured on B200: no gain at any ef; the ~60 extra
+    // instructions per expansion cost what the hidden round trip saves.  The kernel is bound by instruction issue
+    // latency x resident warps as much as by memory latency.)
     // admission against the running farthest distance (:456-465, heap.hh:34-41), all neighbours in one merge
     const uint32_t at = queue_merge(qd, qi, qsize, ef, s_rows, s_dist, cnt, lane);
     if (at < lb) lb = at;
