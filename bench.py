@@ -515,7 +515,7 @@ def main():
     log(f"[rank {rank}] ground truth for {nrec} queries (brute force on the GPU): {time.time() - t0:.1f}s")
     del base
     sweep = []
-    for ef in EF_SWEEP:
+    for ef in sorted(set(EF_SWEEP) | ({args.ef} if args.ef else set())):
         st = ix.search_device(batches[0].data_ptr(), nq, K, ef, ids.data_ptr(), dists.data_ptr(), stream=stream)
         rec = recall_at_k(ids[:nrec], gt)
         sweep.append(dict(ef=ef, recall=round(rec, 4), qps=round(nq / st["kernel_ms"] * 1e3, 1),

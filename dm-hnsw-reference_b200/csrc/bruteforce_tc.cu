@@ -1,10 +1,15 @@
-// bruteforce_tc.cu — exhaustive top-k on the 5th-generation tensor cores (tcgen05 + TMEM + TMA), for d % 64 == 0.
+// bruteforce_tc.cu — exhaustive top-k on the 5th-generation tensor cores (tcgen05 + TMEM + TMA), any dimension (K is
+// zero-padded to a multiple of 64), k <= 16.
 //
 // The dense part of ground-truth generation is the nq x n matrix of inner products.  It is formed by tcgen05.mma in
 // bf16 with fp32 accumulation in TMEM; to keep fp32-grade accuracy every operand is split x = hi + lo (two bf16) and
-// three products are accumulated (hi*hi + hi*lo + lo*hi, error ~2^-16 relative).  The tensor-core pass only GENERATES
-// candidates — per query the 32 best approximate distances of every slice of the base — and an fp32 pass re-ranks them
-// exactly (same arithmetic and tie rule as csrc/bruteforce.cu), so the result is the exact top-k.
+// three products are accumulated (hi*hi + hi*lo + lo*hi, error ~2^-16 |q||x|).  The tensor-core pass only GENERATES
+// candidates — per query the 32 best approximate scores of every slice of the base — and an fp32 pass re-ranks them
+// exactly (same arithmetic and tie rule as csrc/bruteforce.cu).  Exactness is CERTIFIED per query, not assumed: a row that
+// is not a candidate has an approximate score >= the 32nd of its slice, so its true distance is at least that threshold
+// minus the error bound 2 (2^-16 + d 2^-23) |q| max|x|; the k-th exact distance must lie strictly below that for every full slice, and a
+// query for which it does not (a slice that holds more than 32 - k of the true neighbours' near-ties) is answered again
+// by the exact fp32 kernel of csrc/bruteforce.cu.
 //
 // CTA = 128 queries x a slice of base rows, 6 warps: warp 0 issues TMA loads (A = queries hi/lo, B = base rows hi/lo,
 // 128-byte-swizzled K-major tiles of 64 bf16, 2 stages of 96 KB), warp 1 allocates TMEM (2 x 256 columns: the epilogue of
@@ -102,7 +107,7 @@ constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<ui
 struct TcParams {
   uint32_t nq, slab_rows, rows_per_slice, k_blocks, list0;  // list0: first candidate-list slot of this slab
   uint64_t row0;                                            // global id of the slab's first row
-  const float* xnorm;                                       // [slab_rows] |x|^2 (L2) — unused for IP
+  const float* xnorm;                                       // [slab_rows] |x|^2
   float* part_d;                                            // [lists][nq][CAND]
   uint32_t* part_i;
   int ip;
@@ -246,31 +251,39 @@ bf_tc_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_constant__
   }
 }
 
-// x = hi + lo in bf16, and |x|^2 per row
-__global__ void split_bf16_kernel(const float* __restrict__ src, uint64_t rows, uint32_t dim, __nv_bfloat16* __restrict__ hi,
-                                  __nv_bfloat16* __restrict__ lo, float* __restrict__ norm) {
+// x = hi + lo in bf16 (rows zero-padded to dim_pad), |x|^2 per row, and the largest |x|^2 seen (for the error bound)
+__global__ void split_bf16_kernel(const float* __restrict__ src, uint64_t rows, uint32_t dim, uint32_t dim_pad,
+                                  __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, float* __restrict__ norm,
+                                  float* __restrict__ max_norm2) {
   const int lane = threadIdx.x & 31;
   const uint64_t warps = static_cast<uint64_t>(gridDim.x) * (blockDim.x >> 5);
+  float biggest = 0.f;
   for (uint64_t r = blockIdx.x * static_cast<uint64_t>(blockDim.x >> 5) + (threadIdx.x >> 5); r < rows; r += warps) {
     float acc = 0.f;
-    for (uint32_t e = lane; e < dim; e += 32) {
-      const float x = src[r * dim + e];
+    for (uint32_t e = lane; e < dim_pad; e += 32) {
+      const float x = e < dim ? src[r * dim + e] : 0.f;
       const __nv_bfloat16 h = __float2bfloat16_rn(x);
-      hi[r * dim + e] = h;
-      lo[r * dim + e] = __float2bfloat16_rn(x - __bfloat162float(h));
+      hi[r * dim_pad + e] = h;
+      lo[r * dim_pad + e] = __float2bfloat16_rn(x - __bfloat162float(h));
       acc = fmaf(x, x, acc);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, o);
     if (norm && lane == 0) norm[r] = acc;
+    biggest = fmaxf(biggest, acc);
   }
+  // non-negative floats order like their bit patterns
+  if (lane == 0 && biggest > 0.f) atomicMax(reinterpret_cast<int*>(max_norm2), __float_as_int(biggest));
 }
 
 // Exact fp32 re-rank of the candidates of one query (a warp): distance with one fma per element in element order, ties
 // by lower id — the arithmetic of bruteforce.cu — then the k best.
+// Then the certificate (file header): uncertain[q] = 1 unless the k-th exact distance lies strictly below what any
+// non-candidate row can have.
 __global__ void rerank_kernel(const float* __restrict__ base, const float* __restrict__ queries, uint32_t nq, uint32_t dim, int ip,
-                              const uint32_t* __restrict__ part_i, uint32_t lists, uint32_t k, uint32_t* __restrict__ out_i,
-                              float* __restrict__ out_d) {
+                              const uint32_t* __restrict__ part_i, const float* __restrict__ part_d, uint32_t lists, uint32_t k,
+                              const float* __restrict__ max_xnorm2, const float* __restrict__ qnorm2, uint32_t* __restrict__ out_i,
+                              float* __restrict__ out_d, uint8_t* __restrict__ uncertain) {
   extern __shared__ unsigned char sm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t q = blockIdx.x * (blockDim.x >> 5) + warp;
@@ -338,6 +351,38 @@ __global__ void rerank_kernel(const float* __restrict__ base, const float* __res
     out_i[static_cast<size_t>(q) * k + j] = li[j];
     if (out_d) out_d[static_cast<size_t>(q) * k + j] = li[j] == kInvalid ? __int_as_float(0x7f800000) : ld[j];
   }
+  // certificate: score = dist - |q|^2 (L2) resp. dist - 1 (IP); a full slice list hides only rows with score >= its last
+  // entry, up to the error of the split-bf16 products
+  __syncwarp();
+  const float qn2 = qnorm2[q];
+  // |score error| <= 2 (2^-16 + dim 2^-23) |q||x|: the terms the bf16 split drops, plus dim fp32 accumulation steps (worst case)
+  const float eps = (6.1035156e-5f + static_cast<float>(dim) * 2.3841858e-7f) * sqrtf(qn2) * sqrtf(*max_xnorm2) + 1e-30f;
+  const float kth = li[k - 1] == kInvalid ? __int_as_float(0x7f800000) : ld[k - 1];
+  bool bad = false;
+  for (uint32_t l = lane; l < lists; l += 32) {
+    const size_t o = (static_cast<size_t>(l) * nq + q) * CAND;
+    if (part_i[o + CAND - 1] == kInvalid) continue;  // the slice had fewer than CAND rows: all of them are candidates
+    const float floor_d = (ip ? 1.0f : qn2) + part_d[o + CAND - 1] - eps;
+    bad |= !(kth < floor_d);
+  }
+  bad = __any_sync(0xFFFFFFFFu, bad);
+  if (lane == 0) uncertain[q] = bad ? 1 : 0;
+}
+
+__global__ void gather_queries_kernel(const float* __restrict__ src, const uint32_t* __restrict__ which, uint32_t count, uint32_t dim,
+                                      float* __restrict__ dst) {
+  for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < static_cast<uint64_t>(count) * dim;
+       i += static_cast<uint64_t>(gridDim.x) * blockDim.x)
+    dst[i] = src[static_cast<uint64_t>(which[i / dim]) * dim + i % dim];
+}
+__global__ void scatter_results_kernel(const uint32_t* __restrict__ src_i, const float* __restrict__ src_d, const uint32_t* __restrict__ which,
+                                       uint32_t count, uint32_t k, uint32_t* __restrict__ dst_i, float* __restrict__ dst_d) {
+  for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < static_cast<uint64_t>(count) * k;
+       i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+    const uint64_t o = static_cast<uint64_t>(which[i / k]) * k + i % k;
+    dst_i[o] = src_i[i];
+    if (dst_d) dst_d[o] = src_d[i];
+  }
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -368,12 +413,17 @@ bool make_map(CUtensorMap* m, const void* ptr, uint64_t rows, uint32_t dim, uint
 
 }  // namespace
 
-bool bruteforce_tc_supported(uint32_t dim, uint32_t k) { return dim % BK == 0 && dim >= BK && k <= CAND && encode_fn() != nullptr; }
+static unsigned long long g_tc_fallback_queries = 0;
+unsigned long long bruteforce_tc_last_fallbacks() { return g_tc_fallback_queries; }
+
+bool bruteforce_tc_supported(uint32_t dim, uint32_t k) { return dim >= 1 && dim <= 4096 && k <= CAND / 2 && encode_fn() != nullptr; }
 
 cudaError_t bruteforce_tc_launch(const float* d_base, uint64_t n, const float* d_queries, uint32_t nq, uint32_t dim, bool ip,
                                  uint32_t k, uint32_t* d_ids, float* d_dists, int num_sms, cudaStream_t stream) {
   if (nq == 0) return cudaSuccess;
   if (!bruteforce_tc_supported(dim, k)) return cudaErrorNotSupported;
+  g_tc_fallback_queries = 0;
+  const uint32_t dim_pad = (dim + BK - 1) / BK * BK;  // zero-padded K: the padding adds exact zeros to every product
   const uint64_t slab_max = 4ull << 20;  // rows converted to bf16 hi/lo at a time
   const uint32_t qtiles = (nq + BM - 1) / BM;
   const uint32_t n_slabs = static_cast<uint32_t>((n + slab_max - 1) / slab_max);
@@ -383,30 +433,35 @@ cudaError_t bruteforce_tc_launch(const float* d_base, uint64_t n, const float* d
   const uint32_t lists = n_slabs * slices;
 
   __nv_bfloat16 *qh = nullptr, *ql = nullptr, *bh = nullptr, *bl = nullptr;
-  float *xn = nullptr, *part_d = nullptr;
+  float *xn = nullptr, *qn = nullptr, *part_d = nullptr, *maxn = nullptr;
   uint32_t* part_i = nullptr;
+  uint8_t* uncertain = nullptr;
   const uint64_t slab_alloc = std::min<uint64_t>(n, slab_max);
-  cudaError_t e = cudaMalloc(&qh, static_cast<size_t>(nq) * dim * 2);
-  if (e == cudaSuccess) e = cudaMalloc(&ql, static_cast<size_t>(nq) * dim * 2);
-  if (e == cudaSuccess) e = cudaMalloc(&bh, slab_alloc * dim * 2);
-  if (e == cudaSuccess) e = cudaMalloc(&bl, slab_alloc * dim * 2);
+  cudaError_t e = cudaMalloc(&qh, static_cast<size_t>(nq) * dim_pad * 2);
+  if (e == cudaSuccess) e = cudaMalloc(&ql, static_cast<size_t>(nq) * dim_pad * 2);
+  if (e == cudaSuccess) e = cudaMalloc(&bh, slab_alloc * dim_pad * 2);
+  if (e == cudaSuccess) e = cudaMalloc(&bl, slab_alloc * dim_pad * 2);
   if (e == cudaSuccess) e = cudaMalloc(&xn, slab_alloc * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&qn, static_cast<size_t>(nq) * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&maxn, 2 * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&uncertain, nq);
   if (e == cudaSuccess) e = cudaMalloc(&part_d, static_cast<size_t>(lists) * nq * CAND * sizeof(float));
   if (e == cudaSuccess) e = cudaMalloc(&part_i, static_cast<size_t>(lists) * nq * CAND * sizeof(uint32_t));
   if (e == cudaSuccess) e = cudaMemsetAsync(part_i, 0xFF, static_cast<size_t>(lists) * nq * CAND * sizeof(uint32_t), stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(maxn, 0, 2 * sizeof(float), stream);
   const size_t smem = STAGES * STAGE_BYTES + 1024 /*alignment*/ + 256 /*barriers*/ + 2 * BN * sizeof(float);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(bf_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (e == cudaSuccess) {
-    split_bf16_kernel<<<num_sms * 4, 256, 0, stream>>>(d_queries, nq, dim, qh, ql, nullptr);
+    split_bf16_kernel<<<num_sms * 4, 256, 0, stream>>>(d_queries, nq, dim, dim_pad, qh, ql, qn, maxn + 1);
     CUtensorMap mqh, mql;
-    if (!make_map(&mqh, qh, nq, dim, BM) || !make_map(&mql, ql, nq, dim, BM)) e = cudaErrorInvalidValue;
+    if (!make_map(&mqh, qh, nq, dim_pad, BM) || !make_map(&mql, ql, nq, dim_pad, BM)) e = cudaErrorInvalidValue;
     for (uint32_t sl = 0; sl < n_slabs && e == cudaSuccess; ++sl) {
       const uint64_t r0 = sl * slab_max, rows = std::min<uint64_t>(slab_max, n - r0);
-      split_bf16_kernel<<<num_sms * 8, 256, 0, stream>>>(d_base + r0 * dim, rows, dim, bh, bl, xn);
+      split_bf16_kernel<<<num_sms * 8, 256, 0, stream>>>(d_base + r0 * dim, rows, dim, dim_pad, bh, bl, xn, maxn);
       CUtensorMap mbh, mbl;
-      if (!make_map(&mbh, bh, rows, dim, BN) || !make_map(&mbl, bl, rows, dim, BN)) { e = cudaErrorInvalidValue; break; }
+      if (!make_map(&mbh, bh, rows, dim_pad, BN) || !make_map(&mbl, bl, rows, dim_pad, BN)) { e = cudaErrorInvalidValue; break; }
       TcParams p;
-      p.nq = nq; p.slab_rows = static_cast<uint32_t>(rows); p.k_blocks = dim / BK; p.list0 = sl * slices; p.row0 = r0;
+      p.nq = nq; p.slab_rows = static_cast<uint32_t>(rows); p.k_blocks = dim_pad / BK; p.list0 = sl * slices; p.row0 = r0;
       uint32_t per = static_cast<uint32_t>((rows + slices - 1) / slices);
       p.rows_per_slice = (per + BN - 1) / BN * BN;
       p.xnorm = xn; p.part_d = part_d; p.part_i = part_i; p.ip = ip ? 1 : 0;
@@ -415,14 +470,42 @@ cudaError_t bruteforce_tc_launch(const float* d_base, uint64_t n, const float* d
       if (e == cudaSuccess) e = cudaStreamSynchronize(stream);  // the slab buffers are reused
     }
   }
+  std::vector<uint8_t> flags(nq);
   if (e == cudaSuccess) {
     const int warps = 4;
-    rerank_kernel<<<(nq + warps - 1) / warps, warps * 32, warps * (2 * k + 32 * 33 + 32) * sizeof(float), stream>>>(d_base, d_queries, nq, dim, ip ? 1 : 0,
-                                                                                                   part_i, lists, k, d_ids, d_dists);
+    rerank_kernel<<<(nq + warps - 1) / warps, warps * 32, warps * (2 * k + 32 * 33 + 32) * sizeof(float), stream>>>(
+        d_base, d_queries, nq, dim, ip ? 1 : 0, part_i, part_d, lists, k, maxn, qn, d_ids, d_dists, uncertain);
     e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(flags.data(), uncertain, nq, cudaMemcpyDeviceToHost, stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
   }
-  cudaFree(qh); cudaFree(ql); cudaFree(bh); cudaFree(bl); cudaFree(xn); cudaFree(part_d); cudaFree(part_i);
+  cudaFree(qh); cudaFree(ql); cudaFree(bh); cudaFree(bl); cudaFree(xn); cudaFree(qn); cudaFree(maxn); cudaFree(uncertain);
+  cudaFree(part_d); cudaFree(part_i);
+  if (e != cudaSuccess) return e;
+  // queries without a certificate: the exact fp32 kernel answers them again
+  std::vector<uint32_t> which;
+  for (uint32_t q = 0; q < nq; ++q) if (flags[q]) which.push_back(q);
+  g_tc_fallback_queries = which.size();
+  if (!which.empty()) {
+    const uint32_t cnt = static_cast<uint32_t>(which.size());
+    uint32_t *d_which = nullptr, *sub_i = nullptr;
+    float *sub_q = nullptr, *sub_d = nullptr;
+    e = cudaMalloc(&d_which, cnt * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&sub_q, static_cast<size_t>(cnt) * dim * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&sub_i, static_cast<size_t>(cnt) * k * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&sub_d, static_cast<size_t>(cnt) * k * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_which, which.data(), cnt * sizeof(uint32_t), cudaMemcpyHostToDevice, stream);
+    if (e == cudaSuccess) {
+      gather_queries_kernel<<<std::min<uint32_t>(cnt, 1024), 256, 0, stream>>>(d_queries, d_which, cnt, dim, sub_q);
+      e = bruteforce_launch(d_base, n, sub_q, cnt, dim, ip, k, sub_i, sub_d, num_sms, stream);
+    }
+    if (e == cudaSuccess) {
+      scatter_results_kernel<<<std::min<uint32_t>(cnt, 1024), 256, 0, stream>>>(sub_i, sub_d, d_which, cnt, k, d_ids, d_dists);
+      e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    cudaFree(d_which); cudaFree(sub_q); cudaFree(sub_i); cudaFree(sub_d);
+  }
   return e;
 }
 

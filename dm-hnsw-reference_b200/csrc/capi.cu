@@ -463,6 +463,9 @@ void shn_index_free(shn_index* ix) {
   cudaFree(ix->ws.counter); cudaFree(ix->ws.totals);
   ix->ovf.release(); ix->q_stage.release(); ix->dist_stage.release(); ix->id_stage.release();
   for (auto& e : ix->ev) if (e) cudaEventDestroy(e);
+  for (auto& c : ix->ev_chunk) for (auto& e : c) if (e) cudaEventDestroy(e);
+  if (ix->s_in) cudaStreamDestroy(ix->s_in);
+  if (ix->s_out) cudaStreamDestroy(ix->s_out);
   if (ix->ev_last) cudaEventDestroy(ix->ev_last);
   if (ix->stream) cudaStreamDestroy(ix->stream);
   delete ix;
@@ -533,22 +536,60 @@ int shn_search(shn_index* ix, const float* queries, uint64_t nq, uint32_t k, uin
   if (ix->q_stage.ensure(nq * ix->dim) != cudaSuccess || ix->id_stage.ensure(nq * k) != cudaSuccess ||
       ix->dist_stage.ensure(nq * k) != cudaSuccess)
     return fail(SHN_ERR_CUDA, "cannot allocate staging buffers for %llu queries", static_cast<unsigned long long>(nq));
+  // Large batches are cut into chunks: the queries of chunk c+1 travel to the device and the results of chunk c-1 travel
+  // back (each on its own stream, i.e. its own copy engine) while chunk c is searched.  SHN_SEARCH_CHUNKS overrides the count.
+  uint32_t chunks = nq >= (1u << 17) ? 4u : 1u;
+  if (const char* env = std::getenv("SHN_SEARCH_CHUNKS")) chunks = static_cast<uint32_t>(std::max(1, std::min(8, std::atoi(env))));
+  if (chunks > nq) chunks = 1;
+  if (chunks > 1 && !ix->s_in) {
+    CU(cudaStreamCreateWithFlags(&ix->s_in, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&ix->s_out, cudaStreamNonBlocking));
+  }
+  for (uint32_t c = 0; c < chunks; ++c) for (auto& e : ix->ev_chunk[c]) if (!e) CU(cudaEventCreate(&e));
   cudaStream_t s = ix->stream;
+  cudaStream_t s_in = chunks > 1 ? ix->s_in : s, s_out = chunks > 1 ? ix->s_out : s;
+  const uint64_t per = (nq + chunks - 1) / chunks;
   CU(cudaEventRecord(ix->ev[0], s));
-  CU(cudaMemcpyAsync(ix->q_stage.p, queries, nq * ix->dim * sizeof(float), cudaMemcpyHostToDevice, s));
-  rc = run_search(ix, ix->q_stage.p, nq, k, ef, ix->id_stage.p, ix->dist_stage.p, nullptr, s, true, nullptr);
-  if (rc != SHN_OK) return rc;
-  CU(cudaMemcpyAsync(out_ids, ix->id_stage.p, nq * k * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-  if (out_dists) CU(cudaMemcpyAsync(out_dists, ix->dist_stage.p, nq * k * sizeof(float), cudaMemcpyDeviceToHost, s));
+  if (chunks > 1) CU(cudaStreamWaitEvent(s_in, ix->ev[0], 0));  // after whatever the handle's stream was doing with the staging buffers
+  for (uint32_t c = 0; c < chunks; ++c) {
+    const uint64_t q0 = c * per, cnt = std::min<uint64_t>(per, nq - q0);
+    CU(cudaMemcpyAsync(ix->q_stage.p + q0 * ix->dim, queries + q0 * ix->dim, cnt * ix->dim * sizeof(float), cudaMemcpyHostToDevice, s_in));
+    CU(cudaEventRecord(ix->ev_chunk[c][0], s_in));
+  }
+  for (uint32_t c = 0; c < chunks; ++c) {
+    const uint64_t q0 = c * per, cnt = std::min<uint64_t>(per, nq - q0);
+    if (chunks > 1) CU(cudaStreamWaitEvent(s, ix->ev_chunk[c][0], 0));
+    CU(cudaEventRecord(ix->ev_chunk[c][1], s));
+    ix->ws.keep_totals = c > 0;
+    rc = run_search(ix, ix->q_stage.p + q0 * ix->dim, cnt, k, ef, ix->id_stage.p + q0 * k, ix->dist_stage.p + q0 * k, nullptr, s, false, nullptr);
+    ix->ws.keep_totals = false;
+    if (rc != SHN_OK) { cudaStreamSynchronize(s_in); cudaStreamSynchronize(s); cudaStreamSynchronize(s_out); return rc; }
+    CU(cudaEventRecord(ix->ev_chunk[c][2], s));
+    if (chunks > 1) CU(cudaStreamWaitEvent(s_out, ix->ev_chunk[c][2], 0));
+    CU(cudaMemcpyAsync(out_ids + q0 * k, ix->id_stage.p + q0 * k, cnt * k * sizeof(uint32_t), cudaMemcpyDeviceToHost, s_out));
+    if (out_dists) CU(cudaMemcpyAsync(out_dists + q0 * k, ix->dist_stage.p + q0 * k, cnt * k * sizeof(float), cudaMemcpyDeviceToHost, s_out));
+  }
   unsigned long long t[kNumTotals];
   CU(cudaMemcpyAsync(t, ix->ws.totals, sizeof t, cudaMemcpyDeviceToHost, s));
-  CU(cudaEventRecord(ix->ev[3], s));
   CU(cudaStreamSynchronize(s));
+  if (chunks > 1) {
+    CU(cudaEventRecord(ix->ev[3], s_out));
+    CU(cudaStreamSynchronize(s_out));
+    CU(cudaStreamSynchronize(s_in));
+  } else {
+    CU(cudaEventRecord(ix->ev[3], s));
+    CU(cudaStreamSynchronize(s));
+  }
   if (stats) {
-    float h2d = 0.f, ker = 0.f, d2h = 0.f;
-    CU(cudaEventElapsedTime(&h2d, ix->ev[0], ix->ev[1]));
-    CU(cudaEventElapsedTime(&ker, ix->ev[1], ix->ev[2]));
-    CU(cudaEventElapsedTime(&d2h, ix->ev[2], ix->ev[3]));
+    // kernel_ms: the search launches; h2d_ms / d2h_ms: what the copies add in front of the first and behind the last launch
+    float ker = 0.f, h2d = 0.f, d2h = 0.f;
+    for (uint32_t c = 0; c < chunks; ++c) {
+      float ms = 0.f;
+      CU(cudaEventElapsedTime(&ms, ix->ev_chunk[c][1], ix->ev_chunk[c][2]));
+      ker += ms;
+    }
+    CU(cudaEventElapsedTime(&h2d, ix->ev[0], ix->ev_chunk[0][1]));
+    CU(cudaEventElapsedTime(&d2h, ix->ev_chunk[chunks - 1][2], ix->ev[3]));
     fill_stats(ix, t, nq, stats);
     stats->kernel_ms = ker; stats->h2d_ms = h2d; stats->d2h_ms = d2h;
   }
@@ -1002,7 +1043,7 @@ int shn_bruteforce_topk_device(const float* d_base, uint64_t n, const float* d_q
   // SHN_BRUTEFORCE=simt forces the fp32-pipe kernel, =tc the tensor-core one; default: tensor cores when the shape allows
   const char* mode = std::getenv("SHN_BRUTEFORCE");
   const bool want_tc = !(mode && std::strcmp(mode, "simt") == 0) && bruteforce_tc_supported(dim, k);
-  if (mode && std::strcmp(mode, "tc") == 0 && !want_tc) return fail(SHN_ERR_ARG, "tensor-core brute force needs dim %% 64 == 0 and k <= 32");
+  if (mode && std::strcmp(mode, "tc") == 0 && !want_tc) return fail(SHN_ERR_ARG, "tensor-core brute force needs k <= 16 and dim <= 4096");
   cudaError_t e = want_tc ? bruteforce_tc_launch(d_base, n, d_queries, static_cast<uint32_t>(nq), dim, metric == SHN_IP, k, d_out_ids,
                                                  d_out_dists, sms, static_cast<cudaStream_t>(stream))
                           : bruteforce_launch(d_base, n, d_queries, static_cast<uint32_t>(nq), dim, metric == SHN_IP, k, d_out_ids,
@@ -1010,6 +1051,10 @@ int shn_bruteforce_topk_device(const float* d_base, uint64_t n, const float* d_q
   if (e != cudaSuccess) return fail(SHN_ERR_CUDA, "bruteforce: %s", cudaGetErrorString(e));
   return SHN_OK;
 }
+
+// Diagnostic (not in include/shn.h): queries of the last tensor-core brute-force launch that lacked the exactness certificate
+// and were answered by the fp32 kernel.
+unsigned long long shn_debug_bruteforce_fallbacks() { return bruteforce_tc_last_fallbacks(); }
 
 int shn_bruteforce_topk(const float* base, uint64_t n, const float* queries, uint64_t nq, uint32_t dim, shn_metric metric,
                         uint32_t k, uint32_t* out_ids, float* out_dists, int gpu_id) {

@@ -22,6 +22,7 @@ struct SearchWorkspace {
   unsigned long long* totals = nullptr;   // [kNumTotals]
   uint32_t* ovf = nullptr;                // [ovf_slots][ovf_cap], all kInvalid at rest
   uint32_t ovf_cap = 0, ovf_slots = 0;
+  bool keep_totals = false;               // the launch adds to the totals instead of starting from zero (chunked calls)
 };
 
 // Routed I/O (router.cu): the queries of a launch come from this GPU's inbox segments (one per source GPU, already in the
@@ -59,6 +60,7 @@ cudaError_t bruteforce_launch(const float* d_base, uint64_t n, const float* d_qu
 
 // Tensor-core variant (bruteforce_tc.cu): tcgen05 candidate generation (bf16 split operands) + exact fp32 re-rank.
 bool bruteforce_tc_supported(uint32_t dim, uint32_t k);
+unsigned long long bruteforce_tc_last_fallbacks();  // queries of the last launch that lacked the exactness certificate
 cudaError_t bruteforce_tc_launch(const float* d_base, uint64_t n, const float* d_queries, uint32_t nq, uint32_t dim, bool ip,
                                  uint32_t k, uint32_t* d_ids, float* d_dists, int num_sms, cudaStream_t stream);
 

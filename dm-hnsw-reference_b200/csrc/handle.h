@@ -54,6 +54,9 @@ struct shn_index {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_last = nullptr;  // recorded after every search launch: the next launch waits for it
+  // shn_search with host buffers, large batches: the batch is cut into chunks whose copies run on their own streams
+  cudaStream_t s_in = nullptr, s_out = nullptr;
+  cudaEvent_t ev_chunk[8][3] = {};  // per chunk: queries arrived | kernel started | kernel finished
   bool launched = false;
 
   // graph in HBM (graph.h)

@@ -273,8 +273,10 @@ cudaError_t search_launch(const DeviceGraph& g, const SearchConfig& cfg, const f
 
   e = cudaMemsetAsync(ws.counter, 0, sizeof(uint32_t), stream);
   if (e != cudaSuccess) return e;
-  e = cudaMemsetAsync(ws.totals, 0, kNumTotals * sizeof(unsigned long long), stream);
-  if (e != cudaSuccess) return e;
+  if (!ws.keep_totals) {
+    e = cudaMemsetAsync(ws.totals, 0, kNumTotals * sizeof(unsigned long long), stream);
+    if (e != cudaSuccess) return e;
+  }
 
   const int v = chunk_variant(g.dim);
   const bool part = g.world > 1 || g.visit_count != nullptr;

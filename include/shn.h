@@ -48,7 +48,8 @@ typedef struct {
   uint64_t overflow_queries;      /* queries whose visited set spilled to the HBM table (still exact) */
   uint64_t processed;             /* statistics.hh processed */
   double kernel_ms;               /* CUDA-event time of the device work of this call */
-  double h2d_ms, d2h_ms;          /* host<->device copies of this call (0 for the *_device entry points) */
+  double h2d_ms, d2h_ms;          /* what the host<->device copies add in front of the first / behind the last kernel of this call
+                                   * (shn_search cuts large batches into chunks whose copies overlap the search; 0 for *_device) */
   /* partitioned handles only: where the level-0 rows of this call were read from (cache.hits_total = rows_hot +
    * rows_local, cache.misses_total = rows_remote in the reference's JSON) */
   uint64_t rows_hot;              /* replicated hot set in local HBM (the compute-node cache of src/cache/cache.hh) */

@@ -43,11 +43,14 @@ def test_recall_of_the_index_against_gpu_ground_truth(pkg):
     assert datagen.recall(ids, gt) > 0.98
 
 
-@pytest.mark.parametrize("n,nq,dim,k,ip", [(1000, 5, 64, 10, False), (70000, 300, 128, 10, False), (33333, 129, 192, 32, True),
-                                           (5000, 64, 960, 10, False), (300000, 1000, 128, 10, False)])
+@pytest.mark.parametrize("n,nq,dim,k,ip", [(1000, 5, 64, 10, False), (70000, 300, 128, 10, False), (33333, 129, 192, 16, True),
+                                           (5000, 64, 960, 10, False), (300000, 1000, 128, 10, False),
+                                           (50000, 200, 96, 10, False), (40000, 150, 200, 10, True), (3000, 40, 40, 5, False)])
 def test_tensor_core_path_is_exact(pkg, monkeypatch, n, nq, dim, k, ip):
-    """tcgen05 candidate generation (split-bf16, 3 products) + fp32 re-rank returns what the fp32-pipe kernel returns:
-    same ids, same distance bits (both rank with the same arithmetic; the tensor cores only pick candidates)."""
+    """tcgen05 candidate generation (split-bf16, 3 products, K zero-padded to a multiple of 64) + fp32 re-rank returns what the
+    fp32-pipe kernel returns: same ids, same distance bits (both rank with the same arithmetic; the tensor cores only pick
+    candidates, and a query whose candidates cannot be certified complete is answered by the fp32 kernel)."""
+    import ctypes
     base, queries = datagen.base_and_queries(n, nq, dim, normalize=ip)
     monkeypatch.setenv("SHN_BRUTEFORCE", "simt")
     ids_s, d_s = pkg.bruteforce_topk(base, queries, k, ip=ip)
@@ -56,10 +59,34 @@ def test_tensor_core_path_is_exact(pkg, monkeypatch, n, nq, dim, k, ip):
     same = (ids_s == ids_t).all(axis=1)
     assert same.mean() == 1.0, f"{(~same).sum()} of {nq} queries differ"
     assert (d_s.view(np.uint32) == d_t.view(np.uint32)).all()
+    fb = pkg.shn.lib().shn_debug_bruteforce_fallbacks
+    fb.restype = ctypes.c_ulonglong
+    assert fb() <= nq // 10, "the certificate should hold for nearly every query of a well-spread dataset"
+
+
+def test_tensor_core_certificate_catches_what_the_candidates_miss(pkg, monkeypatch):
+    """80 near-copies of every query (distances far below the split-bf16 error of the candidate scores) in ONE slice: the 32
+    candidates of a slice that holds more than 32 of them cannot be proven to contain the 10 nearest, the certificate fails, and the fp32 kernel answers —
+    the result is still exactly the fp32-pipe kernel's."""
+    import ctypes
+    rng = np.random.default_rng(5)
+    nq, dim, k = 8, 128, 10
+    queries = (rng.standard_normal((nq, dim)) * 30).astype(np.float32)
+    near = np.repeat(queries, 80, axis=0) + rng.standard_normal((nq * 80, dim)).astype(np.float32) * 1e-4
+    far = (rng.standard_normal((2000, dim)) * 30).astype(np.float32)
+    base = np.ascontiguousarray(np.concatenate([near, far]), dtype=np.float32)
+    monkeypatch.setenv("SHN_BRUTEFORCE", "simt")
+    ids_s, d_s = pkg.bruteforce_topk(base, queries, k)
+    monkeypatch.setenv("SHN_BRUTEFORCE", "tc")
+    ids_t, d_t = pkg.bruteforce_topk(base, queries, k)
+    assert (ids_s == ids_t).all() and (d_s.view(np.uint32) == d_t.view(np.uint32)).all()
+    fb = pkg.shn.lib().shn_debug_bruteforce_fallbacks
+    fb.restype = ctypes.c_ulonglong
+    assert fb() == nq
 
 
 def test_tensor_core_path_rejects_unsupported_shapes(pkg, monkeypatch):
     monkeypatch.setenv("SHN_BRUTEFORCE", "tc")
     base, queries = datagen.base_and_queries(100, 4, 40)
     with pytest.raises(pkg.ShnError):
-        pkg.bruteforce_topk(base, queries, 5)
+        pkg.bruteforce_topk(base, queries, 17)   # k above CAND / 2: no margin for the certificate

@@ -16,5 +16,8 @@ for mode in ("simt", "tc"):
         torch.cuda.synchronize(); dt = time.time() - t
         if rep == 1: torch.cuda.profiler.stop()
     out[mode] = ids.clone()
+    import ctypes
+    fb = pkg.shn.lib().shn_debug_bruteforce_fallbacks; fb.restype = ctypes.c_ulonglong
+    print(f"{mode}: fallbacks {fb() if mode == 'tc' else 0}", end="  ")
     print(f"{mode}: {dt:.3f}s  {2.0 * n * nq * dim / dt / 1e12:.1f} TFLOP/s (2*n*nq*d)", flush=True)
 print("identical:", bool((out["simt"] == out["tc"]).all()))
