@@ -8,6 +8,7 @@
 // farthest distance, strict '<', visited marked before the distance is computed; distances are summed in the
 // reference's own order (search.cuh), so ids and distances are bit-identical except on exact distance ties.
 #include <cstdio>
+#include <cstdlib>
 
 #include "engine.h"
 #include "search.cuh"
@@ -49,8 +50,18 @@ __host__ __device__ inline size_t warp_smem_bytes(uint32_t q_floats, uint32_t ef
   return kTotalsBytes + (part ? 4ull * list_cap : 0ull) + 4ull * (q_floats + 2 * list_cap + 2 * ef_cap + vis_cap);
 }
 
-template <bool IP, int NCHUNK, bool PART>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, SHN_MIN_BLOCKS) search_kernel(const SearchParams p) {
+// WIDE: the large-ef configuration — 16 rows in flight per warp (4 passes, 128 registers) on 4 CTAs per SM instead of 8 rows on
+// 5.  Measured on B200 (M q/s, narrow / wide): 10 M x 128 at ef 64 / 72 / 100 / 128 / 200: 7.07/6.76, 5.49/5.71, 3.89/4.03, 3.02/3.13,
+// 1.82/1.89; 20 M x 96 at ef 64 / 100 / 128: 7.60/7.11, 4.44/4.33, 3.42/3.33.  The wider waves pay when a row spans four lines and
+// the expansions are long; SHN_WIDE_FROM_EF overrides the crossover (tuning).
+bool use_wide(uint32_t dim, uint32_t ef) {
+  static const int env = [] { const char* e = getenv("SHN_WIDE_FROM_EF"); return e ? atoi(e) : -1; }();
+  if (env >= 0) return ef >= static_cast<uint32_t>(env);
+  return dim >= 128 && ef >= 72;
+}
+template <bool IP, int NCHUNK, bool PART, bool WIDE>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, WIDE ? SHN_MIN_BLOCKS - 1 : SHN_MIN_BLOCKS) search_kernel(const SearchParams p) {
+  constexpr int PASSES = WIDE ? 2 * SHN_PASSES : SHN_PASSES;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -127,7 +138,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, SHN_MIN_BLOCKS) search_ke
     // search_level<without_lock>(ef, level 0) (hnsw.hh:407-476)
     uint32_t c_hot = 0, c_local = 0, c_halo = 0;
     const uint32_t l0_before = c_vl0;
-    beam_search<IP, NCHUNK, PART>(g, s_q, 0, p.ef, qd, qi, qsize, s_rows, s_dist, vis, c_unused, c_vl0, c_l0, c_hot, c_local, c_halo,
+    beam_search<IP, NCHUNK, PART, PASSES>(g, s_q, 0, p.ef, qd, qi, qsize, s_rows, s_dist, vis, c_unused, c_vl0, c_l0, c_hot, c_local, c_halo,
                                   s_read, lane);
 
     // trim to k (:296-298); the reference reports ids in heap-array order, here ascending by distance
@@ -192,18 +203,20 @@ uint32_t pick_vis_cap(uint32_t ef, uint32_t m0) {
 }
 
 template <bool IP, int NCHUNK, bool PART>
-cudaError_t launch_t(const SearchParams& p, int grid, size_t smem, cudaStream_t stream) {
-  cudaError_t e = cudaFuncSetAttribute(search_kernel<IP, NCHUNK, PART>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+cudaError_t launch_t(bool wide, const SearchParams& p, int grid, size_t smem, cudaStream_t stream) {
+  auto kernel = wide ? search_kernel<IP, NCHUNK, PART, true> : search_kernel<IP, NCHUNK, PART, false>;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (e != cudaSuccess) return e;
-  search_kernel<IP, NCHUNK, PART><<<grid, kWarpsPerBlock * 32, smem, stream>>>(p);
+  kernel<<<grid, kWarpsPerBlock * 32, smem, stream>>>(p);
   return cudaGetLastError();
 }
 
 template <bool IP, int NCHUNK, bool PART>
-cudaError_t occupancy_t(size_t smem, int* blocks) {
-  cudaError_t e = cudaFuncSetAttribute(search_kernel<IP, NCHUNK, PART>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+cudaError_t occupancy_t(bool wide, size_t smem, int* blocks) {
+  auto kernel = wide ? search_kernel<IP, NCHUNK, PART, true> : search_kernel<IP, NCHUNK, PART, false>;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (e != cudaSuccess) return e;
-  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, search_kernel<IP, NCHUNK, PART>, kWarpsPerBlock * 32, smem);
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, kernel, kWarpsPerBlock * 32, smem);
 }
 
 // dimensions the kernels are instantiated for at compile time (0 = any dim)
@@ -233,7 +246,7 @@ cudaError_t search_plan(const DeviceGraph& g, const SearchConfig& cfg, uint32_t 
   if (bytes > 227 * 1024) return cudaErrorInvalidValue;
   int blocks = 0;
   const int v = chunk_variant(g.dim);
-  cudaError_t e = DISPATCH(occupancy_t, cfg.ip, part, v, bytes, &blocks);
+  cudaError_t e = DISPATCH(occupancy_t, cfg.ip, part, v, use_wide(g.dim, cfg.ef), bytes, &blocks);
   if (e != cudaSuccess) return e;
   if (blocks < 1) return cudaErrorInvalidConfiguration;
   if (cfg.warps_per_sm > 0) {
@@ -280,7 +293,7 @@ cudaError_t search_launch(const DeviceGraph& g, const SearchConfig& cfg, const f
 
   const int v = chunk_variant(g.dim);
   const bool part = g.world > 1 || g.visit_count != nullptr;
-  return DISPATCH(launch_t, cfg.ip, part, v, p, grid, smem, stream);
+  return DISPATCH(launch_t, cfg.ip, part, v, use_wide(g.dim, cfg.ef), p, grid, smem, stream);
 }
 
 }  // namespace shn

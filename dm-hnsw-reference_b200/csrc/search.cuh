@@ -390,7 +390,7 @@ __device__ __forceinline__ bool visited_test_and_set(VisitedSet& v, uint32_t id,
 // seed entries (unexpanded) and the visited set holds their rows.  Level 0 reads the 2m-wide lists, upper levels the
 // m-wide ones.  Counters: distance computations / nodes visited / lists read on this level.
 // ---------------------------------------------------------------------------------------------------------------
-template <bool IP, int NCHUNK, bool PART = false>
+template <bool IP, int NCHUNK, bool PART = false, int PASSES = SHN_PASSES>
 __device__ __forceinline__ void beam_search(const DeviceGraph& g, const float* s_q, uint32_t level, uint32_t ef, float* qd,
                                             uint32_t* qi, uint32_t& qsize, uint32_t* s_rows, float* s_dist, VisitedSet& vis,
                                             uint32_t& c_dist, uint32_t& c_vis, uint32_t& c_lists, uint32_t& c_hot,
@@ -468,7 +468,7 @@ __device__ __forceinline__ void beam_search(const DeviceGraph& g, const float* s
       }
       __syncwarp();
     }
-    eval_rows<IP, NCHUNK, SHN_PASSES>(g, s_q, PART ? s_read : s_rows, cnt, s_dist, lane);
+    eval_rows<IP, NCHUNK, PASSES>(g, s_q, PART ? s_read : s_rows, cnt, s_dist, lane);
 
     // (Requesting the NEXT expansion's list here, before the merge — the entry is known exactly: the closer of the first
     // unexpanded queue entry and the closest candidate of this list — was measured on B200: no gain at any ef; the ~60 extra
