@@ -193,12 +193,15 @@ uint32_t next_pow2(uint32_t v) {
   return p;
 }
 
-// Shared visited table: sized for the typical query (about 20 x ef nodes are touched at m = 16), the tail spills.
+// Shared visited table: sized for the typical query (about 24 x ef nodes are touched at m = 16), the tail spills.  2048 keys is
+// the measured optimum on B200: 4096 / 8192 keys cost occupancy (ef=64: 4.0 / 1.4 M q/s against 6.0), and even filling exactly
+// the shared memory that 5 CTAs/SM leave (2500 keys, no power of two needed) lost 7 % at ef=64 although it ended the spills
+// there (33 instead of 84 612 overflowing queries per million).
 uint32_t pick_vis_cap(uint32_t ef, uint32_t m0) {
   const uint32_t want = ef * (m0 > 32 ? 40u : 24u);
   uint32_t cap = next_pow2(want);
   if (cap < 1024) cap = 1024;
-  if (cap > 2048) cap = 2048;  // measured: a bigger table costs more in occupancy than its spills cost in HBM probes
+  if (cap > 2048) cap = 2048;
   return cap;
 }
 
@@ -236,17 +239,18 @@ cudaError_t search_plan(const DeviceGraph& g, const SearchConfig& cfg, uint32_t 
   const uint32_t q_floats = g.row_f4 * 4;
   const uint32_t ef_cap = (cfg.ef + 31u) & ~31u;
   const uint32_t list_cap = g.m0 <= 32 ? 32u : 64u;
-  uint32_t vis_cap = cfg.vis_cap ? next_pow2(cfg.vis_cap) : pick_vis_cap(cfg.ef, g.m0);
   const bool part = g.world > 1 || g.visit_count != nullptr;
+  const bool wide = use_wide(g.dim, cfg.ef);
+  uint32_t vis_cap = cfg.vis_cap ? (cfg.vis_cap + 3) / 4 * 4 : pick_vis_cap(cfg.ef, g.m0);
   size_t bytes = kWarpsPerBlock * warp_smem_bytes(q_floats, ef_cap, list_cap, vis_cap, part);
-  while (bytes > 200 * 1024 && vis_cap > 1024) {
-    vis_cap >>= 1;
+  while (bytes > 227 * 1024 && vis_cap > 1024) {
+    vis_cap = vis_cap / 2 / 4 * 4;
     bytes = kWarpsPerBlock * warp_smem_bytes(q_floats, ef_cap, list_cap, vis_cap, part);
   }
   if (bytes > 227 * 1024) return cudaErrorInvalidValue;
   int blocks = 0;
   const int v = chunk_variant(g.dim);
-  cudaError_t e = DISPATCH(occupancy_t, cfg.ip, part, v, use_wide(g.dim, cfg.ef), bytes, &blocks);
+  cudaError_t e = DISPATCH(occupancy_t, cfg.ip, part, v, wide, bytes, &blocks);
   if (e != cudaSuccess) return e;
   if (blocks < 1) return cudaErrorInvalidConfiguration;
   if (cfg.warps_per_sm > 0) {

@@ -339,15 +339,17 @@ __device__ __forceinline__ uint4 lds_bucket(const uint32_t* p) {
 // CAS on the first free slot of the bucket.
 __device__ __forceinline__ bool visited_test_and_set(VisitedSet& v, uint32_t id, bool active, int lane) {
   bool is_new = false;
+  // any number of buckets: the home bucket is the high part of hash x buckets (no power-of-two constraint, so the table can
+  // take exactly the shared memory the launch has left)
   const uint32_t nbuckets = v.cap >> 2;
   if (v.count + 32 <= v.limit) {  // warp-uniform: room for every lane
     if (active) {
-      uint32_t b = hash_row(id) & (nbuckets - 1);
+      uint32_t b = __umulhi(hash_row(id), nbuckets);
       for (;;) {
         const uint4 k = lds_bucket(v.tab + 4 * b);
         if (k.x == id || k.y == id || k.z == id || k.w == id) break;
         const int e = k.x == kInvalid ? 0 : (k.y == kInvalid ? 1 : (k.z == kInvalid ? 2 : (k.w == kInvalid ? 3 : -1)));
-        if (e < 0) { b = (b + 1) & (nbuckets - 1); continue; }
+        if (e < 0) { b = b + 1 == nbuckets ? 0u : b + 1; continue; }
         const uint32_t old = atomicCAS(&v.tab[4 * b + e], kInvalid, id);
         if (old == kInvalid) { is_new = true; break; }
         if (old == id) break;
@@ -358,12 +360,12 @@ __device__ __forceinline__ bool visited_test_and_set(VisitedSet& v, uint32_t id,
   } else {
     bool found = false;
     if (active) {  // the shared table is closed for inserts but still answers lookups
-      uint32_t b = hash_row(id) & (nbuckets - 1);
+      uint32_t b = __umulhi(hash_row(id), nbuckets);
       for (;;) {
         const uint4 k = reinterpret_cast<const uint4*>(v.tab)[b];
         if (k.x == id || k.y == id || k.z == id || k.w == id) { found = true; break; }
         if (k.w == kInvalid) break;  // buckets fill front to back: a free last slot ends the probe sequence
-        b = (b + 1) & (nbuckets - 1);
+        b = b + 1 == nbuckets ? 0u : b + 1;
       }
     }
     if (v.ovf_count + 32 > v.ovf_limit) {
