@@ -146,7 +146,9 @@ __global__ void __launch_bounds__(kBuildWarps * 32, 4) insert_search_kernel(cons
 
     // hnsw.hh:151-231 — connect on every level from min(node_level, top) down to 0
     const uint32_t req0 = __ldg(p.req_base + t);
+    bool any_failed = false;  // visited_reset clears vis.failed: remember an overflow on any level
     for (int lv = static_cast<int>(level); lv >= 0; --lv) {
+      any_failed |= vis.failed;
       visited_reset(vis, lane);
       if (lane == 0) { qd[0] = closest; qi[0] = cur; }
       uint32_t qsize = 1;
@@ -172,7 +174,7 @@ __global__ void __launch_bounds__(kBuildWarps * 32, 4) insert_search_kernel(cons
       __syncwarp();
     }
     t_dist += c_dist;
-    if (vis.failed && lane == 0) atomicAdd(p.totals + 1, 1ull);
+    if ((any_failed || vis.failed) && lane == 0) atomicAdd(p.totals + 1, 1ull);
   }
   if (vis.ovf_count) visited_reset(vis, lane);
   if (lane == 0) atomicAdd(p.totals, t_dist);
@@ -355,6 +357,9 @@ cudaError_t select_probe(const DeviceGraph& g, bool ip, const uint32_t* d_cand_r
 
 cudaError_t build_graph(BuildJob& job, cudaStream_t stream) {
   const uint32_t n = job.n, m = job.g.m;
+  // a back-link request packs its level into the 4 bits above target (30) and source (30): m = 2 or 3 with very many nodes
+  // could reach level 16
+  for (uint32_t l : *job.level_host) if (l > 15) return cudaErrorInvalidValue;
   const bool ip = job.ip;
   const uint32_t d_rt = job.g.dim;
   const int v = (d_rt == 96 || d_rt == 128 || d_rt == 200 || d_rt == 960) ? static_cast<int>(d_rt) : 0;

@@ -314,6 +314,8 @@ int shn_index_build_device(shn_index** out, const float* d_base, const uint32_t*
   job.g = ix->view();
   job.l0_w = ix->d_l0; job.up_w = ix->d_up; job.level_dev = ix->d_level; job.level_host = &level;
   job.n = ix->n; job.efc = ef_construction; job.batch_max = g_build_batch_max; job.batch_div = g_build_batch_div; job.ip = metric == SHN_IP; job.num_sms = ix->num_sms;
+  for (uint32_t l : level)
+    if (l > 15) return bail(fail(SHN_ERR_ARG, "a node drew level %u: the builder supports at most 16 levels (m = %u with this many nodes)", l, m));
   cudaError_t e = build_graph(job, s);
   if (e != cudaSuccess) return bail(fail(SHN_ERR_CUDA, "build_graph: %s", cudaGetErrorString(e)));
   if (job.failed) return bail(fail(SHN_ERR_CAPACITY, "%llu inserts overflowed the visited set", job.failed));
