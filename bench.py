@@ -190,6 +190,7 @@ def parity_at_scale(ix, q_dev, ef, cpu_ids, cpu_distcomps, stream):
     same = (gpu == np.sort(cpu_ids, axis=1)).all(axis=1)
     return dict(queries=int(nq), id_identical_frac=round(float(same.mean()), 6),
                 distcomps_equal=bool(st["distcomps"] == cpu_distcomps),
+                distcomps_rel_diff=float(abs(int(st["distcomps"]) - int(cpu_distcomps)) / max(1, int(cpu_distcomps))),
                 distcomps_gpu=int(st["distcomps"]), distcomps_cpu=int(cpu_distcomps))
 
 
