@@ -54,6 +54,20 @@ def test_missing_dataset_fails_loudly(tmp_path):
     assert r.returncode == 1 and "base or query file missing" in r.stderr
 
 
+def test_argv_of_the_reference_launcher_is_accepted(tmp_path):
+    """scripts/run_node.py:36-67 composes this command line for the compute-node role (benchmark.py sets config.EXECUTABLE);
+    every flag must parse — the run then stops at the missing dataset, not at an option.  What the reference's fetch_*.py
+    scripts read from the JSON (meta.zipf_parameter / label / dataset / compute_threads / compute_nodes,
+    queries.queries_per_sec, cache.cache_size_ratio / hit_rate) is asserted on real runs in the GPU tests below."""
+    (tmp_path / "queries").mkdir()
+    argv = ["--servers", "cluster16", "cluster17", "--threads", "16", "--coroutines", "4", "--data-path", str(tmp_path) + "/",
+            "--query-suffix", "a1.0-500k", "--ef-search", "100", "--ef-construction", "500", "--m", "32", "--k", "10",
+            "--load-index", "--label", "routing", "--no-recall", "--ip-dist", "--cache", "--cache-ratio", "5", "--routing",
+            "--initiator", "--clients", "cluster12", "cluster13"]
+    r = run(*argv)
+    assert r.returncode == 1 and "base or query file missing" in r.stderr, r.stderr
+
+
 def write_bin(path, arr):
     with open(path, "wb") as f:
         np.array(arr.shape, dtype=np.uint32).tofile(f)
