@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(kBuildWarps * 32, 4) insert_search_kernel(cons
   vis.cap = p.vis_cap; vis.limit = p.vis_limit;
   vis.ovf = p.ovf + static_cast<size_t>(blockIdx.x * kBuildWarps + warp) * p.ovf_cap;
   vis.ovf_cap = p.ovf_cap; vis.ovf_limit = p.ovf_limit;
-  vis.count = 0; vis.ovf_count = 0; vis.failed = false;
+  vis.count = 0; vis.ovf_count = 0; vis.failed = false; vis.compact = false;
 
   unsigned long long t_dist = 0;
   const uint32_t m = g.m;

@@ -121,6 +121,12 @@ int download(const shn_index* ix, HostGraph& g) {
   return SHN_OK;
 }
 
+}  // namespace
+int shn::default_vis_compact() {
+  static const int v = [] { const char* e = std::getenv("SHN_VIS_COMPACT"); return e ? std::atoi(e) : 1; }();
+  return v;
+}
+namespace {
 int new_handle(shn_index** out, int gpu_id, shn_metric metric) {
   int sms = 0;
   int rc = select_device(gpu_id, &sms);
@@ -201,7 +207,7 @@ void fill_stats(const shn_index* ix, const unsigned long long* t, uint64_t nq, s
 int run_search(shn_index* ix, const float* d_queries, uint64_t nq, uint32_t k, uint32_t ef, uint32_t* d_ids, float* d_dists,
                uint32_t* d_per_query, cudaStream_t stream, bool timed, const RoutedIo* io) {
   SearchConfig cfg;
-  cfg.k = k; cfg.ef = ef; cfg.ip = ix->metric == SHN_IP; cfg.warps_per_sm = ix->warps_per_sm; cfg.num_sms = ix->num_sms; cfg.vis_cap = ix->vis_cap;
+  cfg.k = k; cfg.ef = ef; cfg.ip = ix->metric == SHN_IP; cfg.warps_per_sm = ix->warps_per_sm; cfg.num_sms = ix->num_sms; cfg.vis_cap = ix->vis_cap; cfg.vis_compact = ix->vis_compact != 0;
   int rc = prepare_workspace(ix, cfg, static_cast<uint32_t>(nq));
   if (rc != SHN_OK) return rc;
   // One launch per handle at a time: the work cursor, the totals and the overflow tables are per handle.  A launch on
@@ -498,6 +504,11 @@ int shn_set_option(shn_index* ix, const char* key, int64_t value) {
   if (std::strcmp(key, "visited_smem_entries") == 0) {
     if (value < 0 || value > 32768) return fail(SHN_ERR_ARG, "visited_smem_entries must be in [0, 32768]");
     ix->vis_cap = static_cast<uint32_t>(value);
+    return SHN_OK;
+  }
+  if (std::strcmp(key, "visited_compact") == 0) {
+    if (value < 0 || value > 1) return fail(SHN_ERR_ARG, "visited_compact is 0 or 1");
+    ix->vis_compact = static_cast<int>(value);
     return SHN_OK;
   }
   return fail(SHN_ERR_ARG, "unknown option '%s'", key);

@@ -41,6 +41,7 @@ struct SearchConfig {
   bool ip;
   int warps_per_sm;  // 0 = auto
   uint32_t vis_cap;  // entries of the shared-memory visited table per warp; 0 = auto
+  bool vis_compact = false;  // 16-bit keys where the graph allows it (<= 2^24 ids, 2048-word table)
   int num_sms;
 };
 

@@ -40,6 +40,7 @@ struct DevBuf {
 
 struct shn_index;
 namespace shn {
+int default_vis_compact();  // SHN_VIS_COMPACT=0/1 overrides the built-in default (tuning)
 // shared by shn_search* (capi.cu) and shn_router_search (router.cu)
 int check_search_args(const shn_index* ix, uint64_t nq, uint32_t k, uint32_t ef);
 int run_search(shn_index* ix, const float* d_queries, uint64_t nq, uint32_t k, uint32_t ef, uint32_t* d_ids, float* d_dists,
@@ -77,6 +78,7 @@ struct shn_index {
   shn::DevBuf<uint32_t> id_stage;
   int warps_per_sm = 0;
   uint32_t vis_cap = 0;
+  int vis_compact = shn::default_vis_compact();  // 16-bit keys in the shared visited table where the graph allows it
   shn_stats build_stats{};
   // partitioned handle (shn_index_partition; graph.h "flat numbering"): d_vec / d_l0 are the bases of two address ranges
   // into which the hot set, this GPU's share, the peers' shares and the halo are mapped; n_ids = size of the id space

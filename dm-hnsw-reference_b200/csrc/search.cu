@@ -39,6 +39,7 @@ struct SearchParams {
   unsigned long long* totals;
   uint32_t* ovf;
   uint32_t vis_cap, vis_limit, ovf_cap, ovf_limit;
+  uint32_t vis_compact;                 // 16-bit keys in the shared visited table (search.cuh visited_compact)
   uint32_t q_floats, ef_cap, list_cap;  // shared-memory strides
   RoutedIo io;
 };
@@ -83,6 +84,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, WIDE ? SHN_MIN_BLOCKS - 1
   vis.ovf = p.ovf + static_cast<size_t>(blockIdx.x * kWarpsPerBlock + warp) * p.ovf_cap;
   vis.ovf_cap = p.ovf_cap; vis.ovf_limit = p.ovf_limit;
   vis.count = 0; vis.ovf_count = 0; vis.failed = false;
+  vis.compact = p.vis_compact != 0;
   if (lane < kNumTotals) s_tot[lane] = 0ull;
   __syncwarp();
 
@@ -284,6 +286,7 @@ cudaError_t search_launch(const DeviceGraph& g, const SearchConfig& cfg, const f
   p.out_ids = d_ids; p.out_dists = d_dists; p.per_query = d_per_query;
   p.counter = ws.counter; p.totals = ws.totals; p.ovf = ws.ovf;
   p.vis_cap = vis_cap; p.vis_limit = vis_cap / 4 * 3;
+  p.vis_compact = (cfg.vis_compact && vis_cap == 2048 && g.n <= (1u << 24)) ? 1u : 0u;
   p.ovf_cap = ws.ovf_cap; p.ovf_limit = ws.ovf_cap / 4 * 3;
   p.q_floats = g.row_f4 * 4; p.ef_cap = (cfg.ef + 31u) & ~31u; p.list_cap = g.m0 <= 32 ? 32u : 64u;
   if (io) p.io = *io;

@@ -319,6 +319,7 @@ struct VisitedSet {
   uint32_t cap, limit, ovf_cap, ovf_limit;
   uint32_t count, ovf_count;  // warp-uniform
   bool failed;
+  bool compact;      // 16-bit keys (visited_compact below); needs cap == 2048 and ids below 2^24
 };
 
 __device__ __forceinline__ uint32_t hash_row(uint32_t h) {  // murmur3 finaliser
@@ -345,11 +346,76 @@ __device__ __forceinline__ uint4 lds_bucket(const uint32_t* p) {
   return k;
 }
 
+// Compact form of the shared table, for graphs of at most 2^24 ids: the same 8 KB hold 4096 keys instead of 2048.  The id goes
+// through a BIJECTION of the 24-bit integers (odd multiplications and xor-shifts, each invertible); the top 9 bits of the result
+// name the home bucket (512 buckets of 16 bytes), the other 15 are the key stored there — bucket and key together still identify
+// the id exactly, so there is no false positive.  A bucket holds 8 keys; a key whose home bucket is full goes to the next bucket
+// with the top bit set ("displaced by one"), and only if that is full as well to the table in HBM.  Buckets only ever fill, so
+// "home (or next) still has room" proves that the key was never pushed further, and the HBM table is consulted only by the
+// few keys whose two buckets are both full.  One 128-bit read + four packed 16-bit compares answer a bucket.
+__device__ __forceinline__ uint32_t mix24(uint32_t h) {
+  h = (h * 0x9E3779u) & 0xFFFFFFu; h ^= h >> 12;
+  h = (h * 0x85EBCBu) & 0xFFFFFFu; h ^= h >> 13;
+  h = (h * 0xC2B2AFu) & 0xFFFFFFu; h ^= h >> 11;
+  return h;
+}
+__device__ __forceinline__ bool visited_compact(VisitedSet& v, uint32_t id, bool active, int lane) {
+  bool is_new = false, spill = false;
+  if (active) {
+    const uint32_t h = mix24(id);
+    const uint32_t home = h >> 15, rem = h & 0x7FFFu;
+    bool done = false;
+#pragma unroll
+    for (uint32_t step = 0; step < 2 && !done; ++step) {
+      const uint32_t key = rem | (step << 15);
+      if (key == 0xFFFFu) break;                      // the one key that would read as "empty": straight to HBM
+      const uint32_t pat = key * 0x10001u;
+      uint32_t* bucket = v.tab + 4u * ((home + step) & 511u);
+      for (;;) {
+        const uint4 k = lds_bucket(bucket);
+        if (__vcmpeq2(k.x, pat) | __vcmpeq2(k.y, pat) | __vcmpeq2(k.z, pat) | __vcmpeq2(k.w, pat)) { done = true; break; }
+        const uint32_t ex = __vcmpeq2(k.x, 0xFFFFFFFFu), ey = __vcmpeq2(k.y, 0xFFFFFFFFu), ez = __vcmpeq2(k.z, 0xFFFFFFFFu),
+                       ew = __vcmpeq2(k.w, 0xFFFFFFFFu);
+        if (!(ex | ey | ez | ew)) break;              // full: try the next bucket (or HBM)
+        const uint32_t w = ex ? 0u : (ey ? 1u : (ez ? 2u : 3u));
+        const uint32_t old = w == 0 ? k.x : (w == 1 ? k.y : (w == 2 ? k.z : k.w));
+        const uint32_t e = w == 0 ? ex : (w == 1 ? ey : (w == 2 ? ez : ew));
+        const uint32_t want = (e & 0xFFFFu) ? ((old & 0xFFFF0000u) | key) : ((old & 0x0000FFFFu) | (key << 16));
+        if (atomicCAS(bucket + w, old, want) == old) { is_new = true; done = true; break; }
+        // another lane changed the word: look at the bucket again
+      }
+    }
+    spill = !done;
+  }
+  v.count += __popc(__ballot_sync(kFull, is_new));
+  if (__any_sync(kFull, spill)) {  // warp-uniform
+    if (v.ovf_count + 32 > v.ovf_limit) {
+      v.failed = true;  // caller reports SHN_ERR_CAPACITY
+    } else {
+      bool added = false;
+      if (spill) {
+        uint32_t s = (hash_row(id) >> 7) & (v.ovf_cap - 1);
+        for (;;) {
+          const uint32_t old = atomicCAS(&v.ovf[s], kInvalid, id);
+          if (old == kInvalid) { added = true; break; }
+          if (old == id) break;
+          s = (s + 1) & (v.ovf_cap - 1);
+        }
+      }
+      is_new |= added;
+      v.ovf_count += __popc(__ballot_sync(kFull, added));
+    }
+  }
+  __syncwarp();
+  return is_new;
+}
+
 // Each lane with active==true offers one id (ids offered together are distinct); returns true for lanes whose
 // id was not in the set (and now is).  The shared table is organised in 16-byte buckets of four keys: one 128-bit
 // read answers "already visited" (about half of all offers) without an atomic, an insert costs that read plus one
 // CAS on the first free slot of the bucket.
 __device__ __forceinline__ bool visited_test_and_set(VisitedSet& v, uint32_t id, bool active, int lane) {
+  if (v.compact) return visited_compact(v, id, active, lane);  // warp-uniform
   bool is_new = false;
   // any number of buckets: the home bucket is the high part of hash x buckets (no power-of-two constraint, so the table can
   // take exactly the shared memory the launch has left)

@@ -114,7 +114,8 @@ uint32_t shn_index_max_level(const shn_index*);  /* build.max_level in the refer
 uint64_t shn_index_hbm_bytes(const shn_index*);  /* device memory held by the handle */
 uint64_t shn_index_dump_bytes(const shn_index*); /* "index_size": bytes the reference would have allocated (rdma_atomics.hh:98) */
 /* Options: "warps_per_sm" (0 = auto): cap on resident query warps per SM; "visited_smem_entries" (0 = auto): size of
- * the per-warp visited table in shared memory (the rest spills to HBM, still exact).  Distances are always summed in the
+ * the per-warp visited table in shared memory (the rest spills to HBM, still exact); "visited_compact" (default 1): 16-bit
+ * keys in that table where the graph allows it (at most 2^24 ids, default table size) — twice the keys per byte, exact.  Distances are always summed in the
  * reference's own order (src/hnsw/distance.hh as compiled, see oracle/hnsw_oracle.c), so results are bit-identical
  * to the reference's except on exact distance ties. */
 int shn_set_option(shn_index*, const char* key, int64_t value);

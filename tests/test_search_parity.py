@@ -4,6 +4,7 @@ decided a comparison on exactly equal distances (oracle `tie` flag) are compared
 import numpy as np
 import pytest
 
+import datagen
 import golden_io
 import hnsw_oracle
 
@@ -173,6 +174,26 @@ def test_live_parity_against_reference_built_index(pkg, m, dim, ip, n):
             if (ct["tie"] == 0).all():
                 assert st["distcomps"] == int(ct["distcomps"].sum())
                 assert st["lists_l0"] == int(ct["lists_l0"].sum()) and st["lists_upper"] == int(ct["lists_upper"].sum())
+
+
+@pytest.mark.parametrize("ef", [64, 200, 900])
+def test_compact_visited_table_is_exact(pkg, ef):
+    """The 16-bit-key form of the shared visited table (search.cuh visited_compact: bijective 24-bit mix, 9 bits of bucket +
+    15 bits of key, one-step displacement, HBM behind it) against the 32-bit form on the same index: same ids, same distance
+    bits, and the same number of distance computations — a visited set that forgot or invented a single node would change it.
+    ef = 900 overflows both forms into the HBM table."""
+    base, queries = datagen.base_and_queries(40000, 300, 32)
+    with pkg.Index.build(base, 16, 100) as ix:
+        ix.set_option("visited_compact", 0)
+        ids0, d0, st0 = ix.search(queries, 10, ef)
+        ix.set_option("visited_compact", 1)
+        ids1, d1, st1 = ix.search(queries, 10, ef)
+    assert (ids0 == ids1).all() and (d0.view(np.uint32) == d1.view(np.uint32)).all()
+    for key in ("distcomps", "visited_nodes_l0", "lists_l0", "lists_upper"):
+        assert st0[key] == st1[key], key
+    if ef == 900:
+        assert st0["overflow_queries"] > 0 and st1["overflow_queries"] > 0
+        assert st1["overflow_queries"] <= st0["overflow_queries"]
 
 
 def test_c1_sift1m_reference_built_id_parity(pkg):
