@@ -562,6 +562,7 @@ int shn_search(shn_index* ix, const float* queries, uint64_t nq, uint32_t k, uin
   cudaStream_t s = ix->stream;
   cudaStream_t s_in = chunks > 1 ? ix->s_in : s, s_out = chunks > 1 ? ix->s_out : s;
   const uint64_t per = (nq + chunks - 1) / chunks;
+  chunks = static_cast<uint32_t>((nq + per - 1) / per);  // chunks that actually hold queries (a forced count on a tiny batch)
   CU(cudaEventRecord(ix->ev[0], s));
   if (chunks > 1) CU(cudaStreamWaitEvent(s_in, ix->ev[0], 0));  // after whatever the handle's stream was doing with the staging buffers
   for (uint32_t c = 0; c < chunks; ++c) {

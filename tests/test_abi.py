@@ -114,3 +114,23 @@ def test_level_recipe_is_capped_and_seeded(pkg):
     assert (pkg.draw_levels(100000, 2, seed=5) == a).all() and not (pkg.draw_levels(100000, 2, seed=6) == a).all()
     top = np.maximum.accumulate(a)
     assert (np.diff(top) <= 1).all()  # never more than one above the current top (hnsw.hh:106)
+
+
+def test_compact_visited_key_is_a_bijection():
+    """search.cuh visited_compact stores 15 bits of mix24(id) in bucket (mix24(id) >> 15): exact only if mix24 is a bijection of
+    the 24-bit integers.  The constants are read from the CUDA source and the whole domain is checked."""
+    import re
+    import numpy as np
+    src = open(os.path.join(ROOT, "dm-hnsw-reference_b200", "csrc", "search.cuh")).read()
+    body = src[src.index("uint32_t mix24(uint32_t h)"):]
+    body = body[:body.index("return h;")]
+    steps = re.findall(r"h = \(h \* (0x[0-9A-Fa-f]+)u\) & 0xFFFFFFu; h \^= h >> (\d+);", body)
+    assert len(steps) == 3, body
+    h = np.arange(1 << 24, dtype=np.uint64)
+    for mul, shift in steps:
+        assert int(mul, 16) % 2 == 1 and 0 < int(shift) < 24
+        h = (h * np.uint64(int(mul, 16))) & np.uint64(0xFFFFFF)
+        h ^= h >> np.uint64(int(shift))
+    assert len(np.unique(h)) == 1 << 24
+    # and the buckets are evenly used: 512 buckets, 32768 ids each
+    assert (np.bincount((h >> np.uint64(15)).astype(np.int64), minlength=512) == 32768).all()
