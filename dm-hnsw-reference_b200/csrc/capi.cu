@@ -892,71 +892,6 @@ int shn_placement_fit(const shn_index* full, int world, uint32_t seed, double sl
   return SHN_OK;
 }
 
-int shn_route_queries(const float* centroids, int world, uint32_t dim, shn_metric metric, const float* d_queries, uint64_t nq,
-                      double slack, uint8_t* dest, int gpu_id) {
-  if (!centroids || !d_queries || !dest) return fail(SHN_ERR_ARG, "null argument");
-  if (world < 1 || world > 8 || dim == 0) return fail(SHN_ERR_ARG, "need 1 <= world <= 8");
-  if (nq == 0) return SHN_OK;
-  if (nq >= kInvalid) return fail(SHN_ERR_ARG, "too many queries");
-  int sms = 0;
-  int rc = select_device(gpu_id, &sms);
-  if (rc != SHN_OK) return rc;
-  const uint32_t pad = (dim + 3) / 4 * 4;
-  // Workspace kept for the life of the process, one per GPU and host thread: cudaMalloc / cudaFree in the per-batch path
-  // were measured at ~0.5 s per call once peers' shares are mapped into the address space (every allocation has to be
-  // propagated to the peer mappings and waits for the peers' kernels).
-  struct RouteWs { int gpu = -1; DevBuf<float> cent, q, dist; cudaStream_t stream = nullptr; std::vector<float> host; };
-  thread_local RouteWs ws;
-  if (ws.gpu != gpu_id) {
-    ws.cent.release(); ws.q.release(); ws.dist.release();
-    if (ws.stream) cudaStreamDestroy(ws.stream);
-    ws.stream = nullptr;
-    ws.gpu = gpu_id;
-  }
-  if (!ws.stream) CU(cudaStreamCreateWithFlags(&ws.stream, cudaStreamNonBlocking));
-  std::vector<float> cent(static_cast<size_t>(world) * pad, 0.f);
-  for (int c = 0; c < world; ++c) std::memcpy(cent.data() + static_cast<size_t>(c) * pad, centroids + static_cast<size_t>(c) * dim, dim * sizeof(float));
-  cudaError_t e = ws.cent.ensure(cent.size());
-  if (e == cudaSuccess) e = ws.dist.ensure(nq * world);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(ws.cent.p, cent.data(), cent.size() * sizeof(float), cudaMemcpyHostToDevice, ws.stream);
-  const float* rows = d_queries;
-  if (e == cudaSuccess && pad != dim) {  // rows must be whole float4s
-    e = ws.q.ensure(nq * pad);
-    if (e == cudaSuccess) e = cudaMemsetAsync(ws.q.p, 0, nq * pad * sizeof(float), ws.stream);
-    if (e == cudaSuccess) e = cudaMemcpy2DAsync(ws.q.p, pad * sizeof(float), d_queries, dim * sizeof(float), dim * sizeof(float), nq, cudaMemcpyDeviceToDevice, ws.stream);
-    rows = ws.q.p;
-  }
-  ws.host.resize(nq * world);
-  std::vector<float>& dist = ws.host;
-  if (e == cudaSuccess) e = centroid_distances(rows, static_cast<uint32_t>(nq), pad / 4, ws.cent.p, world, metric == SHN_IP, ws.dist.p, ws.stream);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(dist.data(), ws.dist.p, dist.size() * sizeof(float), cudaMemcpyDeviceToHost, ws.stream);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(ws.stream);
-  if (e != cudaSuccess) return fail(SHN_ERR_CUDA, "routing: %s", cudaGetErrorString(e));
-  // query_router.hh:356-368: the nearest centroid whose compute node is under its limit for this batch
-  const uint64_t limit = static_cast<uint64_t>((1.0 + slack) * static_cast<double>(nq) / world) + 1;
-  std::vector<uint64_t> histogram(world, 0);
-  for (uint64_t q = 0; q < nq; ++q) {
-    const float* dq = dist.data() + q * world;
-    // nearest first; ties by lower rank.  Only when the nearest is over its limit is the next one looked up.
-    uint32_t tried = 0;
-    int pick = -1, last = 0;
-    for (int round = 0; round < world; ++round) {
-      int best = -1;
-      for (int c = 0; c < world; ++c) {
-        if (tried & (1u << c)) continue;
-        if (best < 0 || dq[c] < dq[best]) best = c;
-      }
-      tried |= 1u << best;
-      last = best;
-      if (histogram[best] < limit) { pick = best; break; }
-    }
-    if (pick < 0) pick = last;  // every rank is over its limit: the farthest one popped last (query_router.hh:356-368)
-    ++histogram[pick];
-    dest[q] = static_cast<uint8_t>(pick);
-  }
-  return SHN_OK;
-}
-
 int shn_index_partition_export(const shn_index* ix, int* fds, uint64_t* sizes, uint64_t* raw_ptrs) {
   if (!ix || ix->world < 2) return fail(SHN_ERR_STATE, "not a partitioned handle");
   CU(cudaSetDevice(ix->gpu));

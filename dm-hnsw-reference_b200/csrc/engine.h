@@ -95,9 +95,6 @@ void kmeans_host(const std::vector<float>& sample, uint32_t count, uint32_t d, i
                  std::vector<float>& centroids);
 cudaError_t balanced_assign(const float4* d_vec, uint32_t n, uint32_t row_f4, const float* d_cent_stored, int k, bool ip,
                             double slack, uint8_t* d_owner, std::vector<uint32_t>& sizes, cudaStream_t s);
-// rows of row_f4 float4 (any consistent element order) against k centroids of the same width -> out[n][k]
-cudaError_t centroid_distances(const float* d_rows, uint32_t n, uint32_t row_f4, const float* d_cent, int k, bool ip,
-                               float* d_out, cudaStream_t s);
 
 // ---- construction (build.cu) ------------------------------------------------------------------------------------
 struct BuildJob {

@@ -178,12 +178,4 @@ cudaError_t balanced_assign(const float4* d_vec, uint32_t n, uint32_t row_f4, co
   return e;
 }
 
-cudaError_t centroid_distances(const float* d_rows, uint32_t n, uint32_t row_f4, const float* d_cent, int k, bool ip,
-                               float* d_out, cudaStream_t s) {
-  const size_t smem = static_cast<size_t>(k) * row_f4 * 16;
-  cudaFuncSetAttribute(centroid_dist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-  centroid_dist_kernel<<<148 * 8, 256, smem, s>>>(reinterpret_cast<const float4*>(d_rows), n, row_f4, d_cent, k, ip, d_out);
-  return cudaGetLastError();
-}
-
 }  // namespace shn

@@ -372,6 +372,52 @@ int shn_router_search(shn_router* r, uint32_t k, uint32_t ef, void* stream, shn_
   return SHN_OK;
 }
 
+// The routing rule alone, for callers that move the queries themselves (parallel.RoutedExchange: one all-to-all each way):
+// dest[q] = the rank query q runs on.  The same two kernels as shn_router_scatter — preference order per query, then the
+// limit-aware assignment in query order — and one copy of nq bytes back to the host.
+int shn_route_queries(const float* centroids, int world, uint32_t dim, shn_metric metric, const float* d_queries, uint64_t nq,
+                      double slack, uint8_t* dest, int gpu_id) {
+  if (!centroids || !d_queries || !dest) return fail(SHN_ERR_ARG, "null argument");
+  if (world < 1 || world > 8 || dim == 0) return fail(SHN_ERR_ARG, "need 1 <= world <= 8");
+  if (slack < 0.) return fail(SHN_ERR_ARG, "slack must be >= 0");
+  if (nq == 0) return SHN_OK;
+  if (nq >= (1ull << 31)) return fail(SHN_ERR_ARG, "too many queries");
+  int sms = 0;
+  int rc = select_device(gpu_id, &sms);
+  if (rc != SHN_OK) return rc;
+  // Workspace kept for the life of the process, one per GPU and host thread: cudaMalloc / cudaFree in the per-batch path
+  // were measured at ~0.5 s per call once peers' shares are mapped into the address space.
+  struct RouteWs { int gpu = -1; DevBuf<float> cent; DevBuf<uint32_t> pref, slot, hist; DevBuf<uint8_t> dest; cudaStream_t stream = nullptr; };
+  thread_local RouteWs ws;
+  if (ws.gpu != gpu_id) {
+    ws.cent.release(); ws.pref.release(); ws.slot.release(); ws.hist.release(); ws.dest.release();
+    if (ws.stream) cudaStreamDestroy(ws.stream);
+    ws.stream = nullptr;
+    ws.gpu = gpu_id;
+  }
+  if (!ws.stream) CU(cudaStreamCreateWithFlags(&ws.stream, cudaStreamNonBlocking));
+  const size_t cent_floats = static_cast<size_t>(world) * dim;
+  cudaError_t e = ws.cent.ensure(cent_floats);
+  if (e == cudaSuccess) e = ws.pref.ensure(nq);
+  if (e == cudaSuccess) e = ws.slot.ensure(nq);
+  if (e == cudaSuccess) e = ws.hist.ensure(8);
+  if (e == cudaSuccess) e = ws.dest.ensure(nq);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(ws.cent.p, centroids, cent_floats * sizeof(float), cudaMemcpyHostToDevice, ws.stream);
+  const size_t smem = cent_floats * sizeof(float);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(route_pref_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  if (e != cudaSuccess) return fail(SHN_ERR_CUDA, "routing: %s", cudaGetErrorString(e));
+  const int grid = static_cast<int>(std::min<uint64_t>((nq + 7) / 8, static_cast<uint64_t>(sms) * 8));
+  route_pref_kernel<<<grid, 256, smem, ws.stream>>>(d_queries, static_cast<uint32_t>(nq), dim, ws.cent.p, world, metric == SHN_IP, ws.pref.p);
+  // query_router.hh:356-368: the nearest centroid whose compute node is under its limit for this batch
+  const uint32_t limit = static_cast<uint32_t>(std::min<double>(static_cast<double>(nq), (1.0 + slack) * static_cast<double>(nq) / world + 1.0));
+  route_assign_kernel<<<1, kChunk, 0, ws.stream>>>(ws.pref.p, static_cast<uint32_t>(nq), world, limit, ws.dest.p, ws.slot.p, ws.hist.p);
+  e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(dest, ws.dest.p, nq, cudaMemcpyDeviceToHost, ws.stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ws.stream);
+  if (e != cudaSuccess) return fail(SHN_ERR_CUDA, "routing: %s", cudaGetErrorString(e));
+  return SHN_OK;
+}
+
 // This rank's landing buffers (device pointers): row q = the k results of the q-th query this rank handed to
 // shn_router_scatter, valid after the barrier that follows every rank's shn_router_search; row stride = the k of that search.
 int shn_router_results(const shn_router* r, uint32_t** d_ids, float** d_dists) {

@@ -146,7 +146,8 @@ int shn_index_partition(shn_index** out, const shn_index* full, int rank, int wo
 int shn_placement_fit(const shn_index* full, int world, uint32_t seed, double slack, float* centroids, uint8_t* d_owner,
                       uint64_t* part_sizes /*[world], may be NULL*/);
 /* dest[q] = the rank query q should run on: its nearest centroid whose rank is still under (1 + slack) * nq / world
- * queries of this batch, in query order (query_router.hh:356-368).  d_queries: device [nq][dim]; dest: host [nq]. */
+ * queries of this batch, in query order (query_router.hh:356-368).  d_queries: device [nq][dim]; dest: host [nq].
+ * Computed on the GPU (the two routing kernels of csrc/router.cu); only the nq destination bytes travel to the host. */
 int shn_route_queries(const float* centroids, int world, uint32_t dim, shn_metric metric, const float* d_queries, uint64_t nq,
                       double slack, uint8_t* dest, int gpu_id);
 /* Halo: a second, per-GPU cache on top of the replicated hot set.  With query routing a GPU's queries stay near its own
